@@ -1,0 +1,53 @@
+#!/usr/bin/env bash
+# build_ref.sh -- TEST INFRASTRUCTURE (oracle).
+#
+# Compiles the reference simulators FROM WHERE THEY LIE (/root/reference, read-only) into
+# shared libraries under oracle/_ref/ (git-ignored, travels to the GPU box with gpurun).
+# The reference's own build system is not used (it has none beyond .vscode/tasks.json).
+# No reference text is written to disk: each source is streamed through `sed` (the
+# mechanical edits listed below) into gcc's stdin between ref_shim_pre.h and
+# ref_shim_post.h.
+#
+# Edits (all outside the state machine):
+#   W  RandomAccessWithNOMA.c:221      nUE sweep 10000..100000 -> the single point ref_nue
+#   B  RandomAccessSimulatorBeta.c:71  same sweep line
+#   B  RandomAccessSimulatorBeta.c:47-57  parameter locals (B has no CLI) read ref_p_* globals
+#
+# Usage: oracle/build_ref.sh [reference_dir]     (default /root/reference)
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ref="${1:-/root/reference}"
+out="$here/_ref"
+inc="$here/../include"
+mkdir -p "$out"
+CC="${CC:-gcc}"
+CFLAGS="-O3 -w -fPIC -shared -std=gnu11 -I$here -I$inc"
+
+if [ ! -f "$ref/RandomAccessWithNOMA.c" ]; then
+    echo "build_ref.sh: $ref not present; keeping prebuilt oracle/_ref (if any)" >&2
+    exit 0
+fi
+
+SWEEP='s/for (int n = 10000; n <= 100000; n += 10000)/for (int n = ref_nue; n <= ref_nue; n += 10000)/'
+
+# ---- W: RandomAccessWithNOMA.c ------------------------------------------------------------
+{ echo '#include "ref_shim_pre.h"'
+  sed -e "$SWEEP" "$ref/RandomAccessWithNOMA.c"
+  echo; echo '#define REF_VARIANT 0'; echo '#include "ref_shim_post.h"'
+} | $CC $CFLAGS -x c - -o "$out/libref_w.so" -lm
+
+# ---- B: RandomAccessSimulatorBeta.c -------------------------------------------------------
+{ echo '#include "ref_shim_pre.h"'
+  sed -e "$SWEEP" \
+      -e 's/int nPreamble = 54; /int nPreamble = ref_p_nPreamble; /' \
+      -e 's/int backoffIndicator = 20;/int backoffIndicator = ref_p_backoff;/' \
+      -e 's/int nGrantUL = 54; /int nGrantUL = ref_p_nGrantUL; /' \
+      -e 's/int maxRarWindow = 6;/int maxRarWindow = ref_p_maxRarWindow;/' \
+      -e 's/int maxMsg2TxCount = 9;/int maxMsg2TxCount = ref_p_maxMsg2TxCount;/' \
+      -e 's/int accessTime = 5; /int accessTime = ref_p_accessTime; /' \
+      -e 's/int distribution = 1;/int distribution = ref_p_distribution;/' \
+      "$ref/RandomAccessSimulatorBeta.c"
+  echo; echo '#define REF_VARIANT 1'; echo '#include "ref_shim_post.h"'
+} | $CC $CFLAGS -x c - -o "$out/libref_b.so" -lm
+
+echo "built: $(ls "$out")"
