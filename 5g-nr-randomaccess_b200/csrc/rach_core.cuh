@@ -1,0 +1,607 @@
+/*
+ * rach_core.cuh -- the per-replication RACH engine (variant W/B dynamics), written once as
+ * "phase" functions that a CUDA thread block executes with __syncthreads() between them
+ * (rach_kernels.cu).  tests/emu/ compiles the same phases for the host and runs them thread
+ * by thread (test infrastructure only; the product library has no CPU path).
+ *
+ * WHAT IT COMPUTES: exactly the per-ms state machine of RandomAccessWithNOMA.c:267-335
+ * (selectPreamble :475-562, preambleCollision :607-665, requestResourceAllocation :667-710,
+ * timerIncrease :712-718, successUEs :720-728) -- bit-identical per-UE outcomes under the
+ * Philox draw tape (include/rach_tape.h) -- but NOT by touching every UE every ms.
+ *
+ * HOW (event-driven restatement):
+ *  * A UE in the Msg1 phase lives in exactly one 16-byte RECORD that sits in the calendar
+ *    bucket of the ms in which its RAR window will expire ("move time" m).  Between two moves
+ *    nothing about the UE changes that cannot be derived from (txTime, m): once it has
+ *    transmitted at txTime=X it is postponed every ms (W:647 or W:658) until it is granted
+ *    or rarWindow reaches maxRarWindow at m = X + Wn - 1 (W:493-496).
+ *  * Per preamble p and move time m a COHORT entry in shared memory holds the number of
+ *    such UEs and the lowest UE index among them.  The UEs visible to a collision scan at
+ *    ms T (active==1 && txTime==T, W:615) are the cohorts m in [T, T+Wn-1].
+ *  * Index order (the reference walks UEs 0..n-1 sequentially, W:302) is reproduced through
+ *    the index of the FIRST scan of each preamble class in the ms,
+ *        s[p] = min( lowest visible non-mover of p,  lowest UE that re-transmits in this very
+ *                    ms into p ("lander": backoff draw 0, W:540-549) ),
+ *    members of p above s[p] are postponed before their turn (which changes the base of the
+ *    limit-branch backoff, W:516), movers below s[p] have left before the scan (group size),
+ *    later landers scan alone, and UL grants go to singleton scans in index order (W:639-641).
+ *  * Msg3 (W:667-710) is a second small calendar.
+ *
+ * Every function cites the reference lines it restates.
+ */
+#ifndef RACH_CORE_CUH
+#define RACH_CORE_CUH
+
+#include <stddef.h>
+#include <stdint.h>
+#include "rach_tape.h"
+
+#ifdef __CUDACC__
+#define RA_HD __host__ __device__ __forceinline__
+#else
+#define RA_HD static inline
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = {a, b, c, d}; return r; }
+#endif
+
+typedef unsigned long long ra_u64;
+
+#define RA_INF32 0xFFFFFFFFu
+#define RA_INF64 0xFFFFFFFFFFFFFFFFull
+#define RA_DEAD  0xFFFFFFFFu
+#define RA_M3RING 64
+#define RA_DUMP_W 16
+
+/* ---- atomics: CUDA on the device, plain read-modify-write in the host emulator ---------- */
+#ifdef __CUDA_ARCH__
+#define RA_AADD(p, v)   atomicAdd((p), (v))
+#define RA_AMIN(p, v)   atomicMin((p), (v))
+#else
+template <class T> static inline T ra_emu_add(T* p, T v) { T o = *p; *p = o + v; return o; }
+template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
+#define RA_AADD(p, v)   ra_emu_add((p), (v))
+#define RA_AMIN(p, v)   ra_emu_min((p), (v))
+#endif
+
+/* ---- one parameter point, device view ---------------------------------------------------- */
+struct RaPointDev {
+    int nUE, P, BI, G, Wn, M, A, maxTime;
+    int geometry, R, nOcc, pad;
+    ra_u64 seed;
+    const int* arrCum;        /* [nOcc] activeCheck after the arrival step of ms occ*A (W:280-292) */
+};
+
+/* ---- per-CTA global workspace ------------------------------------------------------------ */
+struct RaWork {
+    uint4*    bucket;         /* [R][cap]   move calendar                                  */
+    uint4*    msg3;           /* [RA_M3RING][cap3]  Msg3 calendar                           */
+    uint4*    landerRec;      /* [cap]  UEs re-transmitting in the current ms               */
+    unsigned* landerMeta;     /* [cap]  bit0: member of its class at start of ms; bits 8..: late joins */
+    uint4*    uncertain;      /* [cap]  movers below the natural leader: pos, idx, p0|limit<<31 */
+    uint4*    c3;             /* [cap]  limit movers that land iff not postponed: idx,p0,pnew,landed */
+    ra_u64*   singles;        /* [cap]  singleton scans of the ms: idx<<32 | ref            */
+    uint4*    e1Rec;          /* [cap3] Msg3 restarts that land on the current ms (W:693)   */
+    unsigned* e1Meta;         /* [cap3] 1 = absorbed by a later scan                        */
+    int cap, cap3;
+};
+
+/* ---- per-CTA shared state ---------------------------------------------------------------- */
+struct RaShared {
+    unsigned* cnt;            /* [R*P] cohort size                                          */
+    ra_u64*   minIP;          /* [R*P] lowest (idx<<32 | pos in bucket) of the cohort        */
+    unsigned* bcount;         /* [R]   records in each move bucket                          */
+    unsigned* m3count;        /* [RA_M3RING]                                                */
+    unsigned *N, *l1, *l1pos, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each      */
+    int T, grantCheck, activeCheck, acOld, nArr, done, simTime, overflow;
+    unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
+    unsigned nSuccess, noGrant;
+    ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
+};
+
+/* per-thread counters, folded into RaShared at the end of the replication */
+struct RaAcc { unsigned contFailed, collP, txop, collScans, totScans; };
+
+struct RaJob {
+    const RaPointDev* pt;
+    unsigned rep;             /* tape replication id                                        */
+    int* dump;                /* [nUE][16] or NULL                                          */
+};
+
+/* ---- record packing ---------------------------------------------------------------------- */
+/* x: idx   y: txTime   z: timerStart | failCount<<16   w: preamble | mrc<<8 | ptc<<16 | flag<<31
+ * flag: move bucket: 1 = stale (invisible);  Msg3 calendar: 1 = second visit (connectionRequest 48) */
+RA_HD unsigned ra_w3(unsigned p, unsigned mrc, unsigned ptc, unsigned flag) {
+    return (p & 0xFFu) | ((mrc & 0xFFu) << 8) | ((ptc & 0x7FFFu) << 16) | (flag << 31);
+}
+RA_HD unsigned ra_rec_p(const uint4& r)    { return r.w & 0xFFu; }
+RA_HD unsigned ra_rec_mrc(const uint4& r)  { return (r.w >> 8) & 0xFFu; }
+RA_HD unsigned ra_rec_ptc(const uint4& r)  { return (r.w >> 16) & 0x7FFFu; }
+RA_HD unsigned ra_rec_flag(const uint4& r) { return r.w >> 31; }
+RA_HD unsigned ra_rec_ts(const uint4& r)   { return r.z & 0xFFFFu; }
+RA_HD unsigned ra_rec_fail(const uint4& r) { return r.z >> 16; }
+RA_HD unsigned ra_z(unsigned ts, unsigned fail) { return (ts & 0xFFFFu) | (fail << 16); }
+
+/* slot alignment, W:518-527 (= W:544-553, W:688-697) */
+RA_HD int ra_align(int subTime, int A) {
+    int r = subTime % A;
+    if (r == 0) return subTime + 1;
+    if (r == 1) return subTime;
+    return subTime + (A - r + 1);
+}
+
+RA_HD rach_u32x4 ra_draws(const RaJob& job, unsigned ue, int ms) {
+    return rach_tape_block(job.pt->seed, job.rep, ue, (unsigned)ms, 0u, RACH_TAPE_TAG_UE);
+}
+
+RA_HD unsigned ra_first_scan(const RaShared& s, unsigned p) {     /* s[p] of the header comment */
+    unsigned a = s.l1[p], b = s.l2[p];
+    return a < b ? a : b;
+}
+
+/* append a record to move bucket `m`; returns its position */
+RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
+    unsigned slot = (unsigned)m & (unsigned)(pt.R - 1);
+    unsigned pos = RA_AADD(&s.bcount[slot], 1u);
+    if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
+    w.bucket[(size_t)slot * w.cap + pos] = rec;
+    return pos;
+}
+
+/* a UE (re)enters the Msg1 phase with transmission time X = rec.y > now: visible from X on,
+ * its RAR window expires at X + Wn - 1 (rarWindow is 1 at X, W:493) */
+RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec) {
+    int m = (int)rec.y + pt.Wn - 1;
+    unsigned pos = ra_bucket_push(pt, w, s, m, rec);
+    unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
+    RA_AADD(&s.cnt[c], 1u);
+    RA_AMIN(&s.minIP[c], ((ra_u64)rec.x << 32) | pos);
+}
+
+/* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old
+ * txTime, or a Msg3 restart landing on `now`, W:693): invisible to scans, rarWindow counts
+ * from 0 at `now`, so it expires at now + Wn */
+RA_HD void ra_park_stale(const RaPointDev& pt, const RaWork& w, RaShared& s, int now, uint4 rec) {
+    rec.w |= 0x80000000u;
+    ra_bucket_push(pt, w, s, now + pt.Wn, rec);
+}
+
+RA_HD void ra_msg3_push(const RaWork& w, RaShared& s, int due, const uint4& rec) {
+    unsigned slot = (unsigned)due & (RA_M3RING - 1);
+    unsigned pos = RA_AADD(&s.m3count[slot], 1u);
+    if (pos >= (unsigned)w.cap3) { s.overflow = 1; return; }
+    w.msg3[(size_t)slot * w.cap3 + pos] = rec;
+}
+
+RA_HD void ra_lander_push(const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
+    unsigned l = RA_AADD(&s.nLanders, 1u);
+    if (l >= (unsigned)w.cap) { s.overflow = 1; return; }
+    w.landerRec[l] = rec; w.landerMeta[l] = member;
+}
+
+/* ---- dump helpers (DUMP builds only) ------------------------------------------------------ */
+RA_HD void ra_dump_init_row(int* d) {           /* calloc + initialUE, W:229,374-381 */
+    for (int k = 0; k < RA_DUMP_W; ++k) d[k] = 0;
+    d[0] = -1; d[1] = -1; d[2] = -1; d[6] = -1; d[15] = -1;
+}
+
+/* sector of activateUEs, W:392-410, from the first activation draw */
+RA_HD int ra_sector(int r31) {
+    float pi = 3.14;
+    float theta = (float)r31 / (float)(2147483647) * 2 * pi;
+    if (theta >= 0 && theta < ((1. / 3.) * pi)) return 0;
+    else if (theta >= ((1. / 3.) * pi) && theta < ((2. / 3.) * pi)) return 1;
+    else if (theta >= ((2. / 3.) * pi) && theta < 3.14) return 2;
+    else if (theta >= pi && theta < ((4. / 3.) * pi)) return 3;
+    else if (theta >= ((4. / 3.) * pi) && theta < ((5. / 3.) * pi)) return 4;
+    return 5;
+}
+
+/* =========================================================================================
+ * Job start: empty calendars and cohort tables (calloc + initialUE, W:229-234).
+ * ========================================================================================= */
+template <bool DUMP>
+RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
+    const RaPointDev& pt = *job.pt;
+    for (int i = tid; i < pt.R * pt.P; i += nt) { s.cnt[i] = 0; s.minIP[i] = RA_INF64; }
+    for (int i = tid; i < pt.R; i += nt) s.bcount[i] = 0;
+    for (int i = tid; i < RA_M3RING; i += nt) s.m3count[i] = 0;
+    if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
+    if (tid == 0) {
+        s.T = 0; s.grantCheck = 0; s.activeCheck = 0; s.done = 0; s.simTime = pt.maxTime; s.overflow = 0;
+        s.nSuccess = 0; s.noGrant = 0;
+        s.txSum = s.delaySum = s.failSum = s.contFailed = s.collP = s.txop = s.collScans = s.totScans = 0;
+    }
+}
+
+/* =========================================================================================
+ * Phase 0 -- start of ms T: grant reset (W:268-269), arrival gate (W:276-292), per-class
+ * view of the visible cohorts.
+ * ========================================================================================= */
+RA_HD void ra_phase0(const RaJob& job, RaShared& s, int tid, int nt) {
+    const RaPointDev& pt = *job.pt;
+    const int T = s.T, P = pt.P, Wn = pt.Wn;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    for (int p = tid; p < P; p += nt) {
+        unsigned n = 0; ra_u64 best = RA_INF64; unsigned bestm = 0;
+        for (int d = 0; d < Wn; ++d) {
+            unsigned m = ((unsigned)(T + d) & Rm);
+            n += s.cnt[m * P + p];
+            if (d > 0) { ra_u64 v = s.minIP[m * P + p]; if (v < best) { best = v; bestm = m; } }
+        }
+        s.N[p] = n;
+        s.l1[p] = (unsigned)(best >> 32); s.l1pos[p] = (unsigned)best; s.l1m[p] = bestm;
+        s.l2[p] = RA_INF32; s.before[p] = 0; s.extraFirst[p] = 0; s.clsSize[p] = 0;
+    }
+    if (tid == 0) {
+        if (T % 5 == 0) s.grantCheck = 0;                       /* literal 5, W:268 */
+        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32;
+        s.acOld = s.activeCheck;
+        if (T % pt.A == 0 && s.activeCheck != pt.nUE) s.activeCheck = pt.arrCum[T / pt.A];
+        s.nArr = s.activeCheck - s.acOld;
+        s.nMov = s.bcount[(unsigned)T & Rm];
+        s.nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
+    }
+}
+
+/* =========================================================================================
+ * Phase 1 -- one pass over the UEs that have an event in ms T (item = work index):
+ *   [0, nMov)            movers (bucket T): rarWindow reaches maxRarWindow, W:496-558
+ *   [nMov, +nArr)        arrivals: activateUEs + first selectPreamble, W:294-298,383-394,477-487
+ *   [.., +nM3)           Msg3 due: requestResourceAllocation, W:667-710
+ * ========================================================================================= */
+template <bool DUMP>
+RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
+    const RaPointDev& pt = *job.pt;
+    const int T = s.T;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    if (item < s.nMov) {
+        /* ---------------- mover ---------------- */
+        uint4 rec = w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item];
+        if (rec.x == RA_DEAD) return;
+        const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
+        unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
+        /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
+        const bool uncertain = !stale && idx < s.l1[p0];
+        rach_u32x4 d = ra_draws(job, idx, T);
+        if ((int)mrc < pt.M) {
+            /* retry branch, W:532-558: outcome does not depend on being postponed */
+            int tmp = (int)(d.v[0] >> 1) % pt.BI;
+            int X = ra_align(T + tmp, pt.A);
+            mrc++; ptc++;
+            if (ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
+            uint4 nr = make_uint4(idx, (unsigned)X, rec.z, ra_w3(p0, mrc, ptc, 0));
+            if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 4] = X;          /* secondTxTime, W:557 */
+            if (uncertain) {
+                unsigned u = RA_AADD(&s.nUnc, 1u);
+                w.uncertain[u] = make_uint4(item, idx, p0, 0);
+            }
+            if (X == T) {                                   /* backoff 0 on a tx slot: transmits now */
+                RA_AMIN(&s.l2[p0], idx);
+                ra_lander_push(w, s, nr, stale ? 0u : 1u);
+            } else {
+                ra_schedule(pt, w, s, nr);
+            }
+        } else {
+            /* limit branch, W:498-531: subTime = CURRENT txTime + tmp (W:516) */
+            acc.contFailed++;
+            unsigned pnew = (d.v[0] >> 1) % (unsigned)pt.P;
+            int tmp = (int)(d.v[1] >> 1) % pt.BI;
+            unsigned fail = ra_rec_fail(rec) + 1;
+            if (fail > 0xFFFFu) s.overflow = 2;
+            if (uncertain) {                                /* txTime is T or T+1: decided in phase 3 */
+                unsigned u = RA_AADD(&s.nUnc, 1u);
+                w.uncertain[u] = make_uint4(item, idx, p0 | 0x80000000u, 0);
+                if (ra_align(T + tmp, pt.A) == T) {
+                    unsigned c = RA_AADD(&s.nC3, 1u);
+                    w.c3[c] = make_uint4(idx, p0, pnew, 0);
+                }
+                return;
+            }
+            int base = stale ? (int)rec.y : T + 1;          /* visible and above the leader: postponed */
+            int X = ra_align(base + tmp, pt.A);
+            uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, 1, 0));
+            if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;       /* firstTxTime, W:510 */
+            if (X == T) {                                   /* only from an old txTime */
+                RA_AMIN(&s.l2[pnew], idx);
+                ra_lander_push(w, s, nr, 0u);
+            } else if (X > T) {
+                ra_schedule(pt, w, s, nr);
+            } else {
+                ra_park_stale(pt, w, s, T, nr);
+            }
+        }
+        return;
+    }
+    item -= s.nMov;
+    if (item < (unsigned)s.nArr) {
+        /* ---------------- arrival, W:383-394 + first draw W:477-487 ---------------- */
+        unsigned idx = (unsigned)s.acOld + item;
+        rach_u32x4 d = ra_draws(job, idx, T);
+        unsigned p = (d.v[pt.geometry ? 2 : 0] >> 1) % (unsigned)pt.P;
+        uint4 nr = make_uint4(idx, (unsigned)(T + 1), ra_z((unsigned)T, 0), ra_w3(p, 0, 1, 0));
+        if (DUMP) {
+            int* row = job.dump + (size_t)idx * RA_DUMP_W;
+            row[3] = T + 1; row[7] = 1;
+            row[15] = pt.geometry ? ra_sector((int)(d.v[0] >> 1)) : -1;
+        }
+        ra_schedule(pt, w, s, nr);
+        return;
+    }
+    item -= (unsigned)s.nArr;
+    if (item < s.nM3) {
+        /* ---------------- Msg3 / Msg4, W:667-710 ---------------- */
+        uint4 rec = w.msg3[(size_t)((unsigned)T & (RA_M3RING - 1)) * w.cap3 + item];
+        const unsigned idx = rec.x;
+        rach_u32x4 d = ra_draws(job, idx, T);
+        if (ra_rec_flag(rec) == 0) {                        /* connectionRequest 0 -> 1 < 48 */
+            if (rach_msg3_success((int)(d.v[0] >> 1))) {
+                unsigned timer = (unsigned)T - ra_rec_ts(rec) + 6;         /* W:674 */
+                RA_AADD(&s.nSuccess, 1u);
+                RA_AADD(&s.txSum, (ra_u64)ra_rec_ptc(rec));
+                RA_AADD(&s.delaySum, (ra_u64)timer);
+                RA_AADD(&s.failSum, (ra_u64)ra_rec_fail(rec));
+                if (DUMP) {
+                    int* row = job.dump + (size_t)idx * RA_DUMP_W;
+                    row[0] = (int)timer; row[1] = 0; row[2] = T; row[5] = 0;
+                    row[6] = (int)ra_rec_p(rec); row[10] = (int)ra_rec_ptc(rec); row[11] = 1;
+                    row[12] = 1; row[13] = 1; row[14] = (int)ra_rec_fail(rec);
+                }
+            } else {                                        /* W:678-679 */
+                rec.y = (unsigned)(T + 48); rec.w |= 0x80000000u;
+                ra_msg3_push(w, s, T + 48, rec);
+            }
+        } else {
+            /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
+            acc.contFailed++;
+            int tmp = (int)(d.v[0] >> 1) % pt.BI;
+            int X = ra_align(T + tmp, 5);
+            unsigned pnew = (d.v[1] >> 1) % (unsigned)pt.P;
+            unsigned fail = ra_rec_fail(rec) + 1;
+            if (fail > 0xFFFFu) s.overflow = 2;
+            uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, ra_rec_ptc(rec), 0));
+            if (X == T) {                                   /* visible to later scanners, never scans */
+                unsigned e = RA_AADD(&s.nE1, 1u);
+                w.e1Rec[e] = nr; w.e1Meta[e] = 0;
+            } else {
+                ra_schedule(pt, w, s, nr);
+            }
+        }
+    }
+}
+
+/* =========================================================================================
+ * Phase 2 (one thread, only if nC3 > 0) -- limit-branch movers that would re-transmit now if
+ * nobody has postponed them: decide in index order (a landing is itself a scan of its new
+ * class and postpones the members above it).
+ * ========================================================================================= */
+RA_HD void ra_phase2_serial(const RaWork& w, RaShared& s) {
+    const unsigned n = s.nC3;
+    for (unsigned i = 0; i < n; ++i) {                      /* selection by ascending idx */
+        unsigned best = i;
+        for (unsigned j = i + 1; j < n; ++j) if (w.c3[j].x < w.c3[best].x) best = j;
+        uint4 c = w.c3[best]; w.c3[best] = w.c3[i];
+        if (c.x < ra_first_scan(s, c.y)) {                  /* not postponed: lands on pnew */
+            c.w = 1;
+            if (c.x < s.l2[c.z]) s.l2[c.z] = c.x;
+        }
+        w.c3[i] = c;
+    }
+}
+
+/* =========================================================================================
+ * Phase 3 -- movers below the natural leader of their class, now that s[] is final.
+ * ========================================================================================= */
+template <bool DUMP>
+RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, unsigned u) {
+    const RaPointDev& pt = *job.pt;
+    const int T = s.T;
+    const uint4 e = w.uncertain[u];
+    const unsigned idx = e.y, p0 = e.z & 0xFFu;
+    const unsigned sp = ra_first_scan(s, p0);
+    if (idx < sp) RA_AADD(&s.before[p0], 1u);              /* left the class before its first scan */
+    if (!(e.z >> 31)) return;
+    /* limit branch, W:498-531 */
+    uint4 rec = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + e.x];
+    rach_u32x4 d = ra_draws(job, idx, T);
+    unsigned pnew = (d.v[0] >> 1) % (unsigned)pt.P;
+    int tmp = (int)(d.v[1] >> 1) % pt.BI;
+    int base = T + (idx > sp ? 1 : 0);                      /* postponed by the first scan, W:658 */
+    int X = ra_align(base + tmp, pt.A);
+    uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, ra_rec_fail(rec) + 1), ra_w3(pnew, 0, 1, 0));
+    if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;
+    if (X == T) ra_lander_push(w, s, nr, pnew == p0 ? 1u : 0u);   /* s.l2 already holds it (phase 2) */
+    else ra_schedule(pt, w, s, nr);                         /* X > T always: base >= T */
+}
+
+/* =========================================================================================
+ * Phase 3b (only if nE1 > 0) -- a Msg3 restart that landed on T at index k is counted by the
+ * first scan of its class at an index above k (W:613-621), which postpones it.
+ * ========================================================================================= */
+RA_HD void ra_phase3b_item(const RaWork& w, RaShared& s, unsigned e) {
+    const uint4 r = w.e1Rec[e];
+    const unsigned k = r.x, q = ra_rec_p(r);
+    unsigned bestIdx = RA_INF32, bestRef = RA_INF32;
+    unsigned sq = ra_first_scan(s, q);
+    if (sq != RA_INF32 && sq > k && sq == s.l1[q]) { bestIdx = sq; bestRef = 0x80000000u | q; }
+    for (unsigned l = 0; l < s.nLanders; ++l) {
+        const uint4 lr = w.landerRec[l];
+        if (ra_rec_p(lr) == q && lr.x > k && lr.x < bestIdx) { bestIdx = lr.x; bestRef = l; }
+    }
+    if (bestIdx == RA_INF32) return;
+    w.e1Meta[e] = 1;
+    if (bestRef & 0x80000000u) RA_AADD(&s.extraFirst[q], 1u);
+    else RA_AADD(&w.landerMeta[bestRef], 256u);
+}
+
+/* =========================================================================================
+ * Phase 4 -- the collision scans of ms T, W:607-665.
+ *   class items  [0, P):        first scan by the natural leader (a visible non-mover)
+ *   lander items [P, P+nLanders): scan by a UE that re-transmits in this ms
+ * ========================================================================================= */
+RA_HD void ra_count_scan(RaAcc& acc, unsigned size) {
+    acc.totScans++;                                         /* B:334,351 */
+    if (size == 1) { acc.txop++; }                          /* W:625 */
+    else { acc.collP += size; acc.txop += size; acc.collScans++; }   /* W:650-652, B:349 */
+}
+
+RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
+    if (item < (unsigned)pt.P) {
+        const unsigned q = item;
+        const unsigned sq = ra_first_scan(s, q);
+        if (sq == RA_INF32 || sq != s.l1[q]) return;        /* no scan, or a lander scans first */
+        unsigned size = s.N[q] - s.before[q] + s.extraFirst[q];
+        s.clsSize[q] = size;
+        ra_count_scan(acc, size);
+        if (size == 1) {
+            unsigned k = RA_AADD(&s.nSingles, 1u);
+            w.singles[k] = ((ra_u64)sq << 32) | (0x80000000u | q);
+        }
+        return;
+    }
+    const unsigned l = item - (unsigned)pt.P;
+    if (l >= s.nLanders) return;
+    const uint4 r = w.landerRec[l];
+    const unsigned q = ra_rec_p(r), meta = w.landerMeta[l];
+    unsigned size;
+    if (r.x == ra_first_scan(s, q)) size = s.N[q] - s.before[q] + ((meta & 1u) ? 0u : 1u) + (meta >> 8);
+    else size = 1u + (meta >> 8);
+    ra_count_scan(acc, size);
+    if (size == 1) {
+        unsigned k = RA_AADD(&s.nSingles, 1u);
+        w.singles[k] = ((ra_u64)r.x << 32) | l;
+    } else {
+        w.landerMeta[l] = meta | 2u;                        /* collided */
+    }
+}
+
+/* =========================================================================================
+ * Phase 5 (one thread / warp) -- UL grants: the first G-1-grantCheck singleton scans in UE
+ * index order are granted (strict '<' after the increment, W:639-641).
+ * tau = highest granted index (RA_INF32: all, 0 with nobody granted handled by flag).
+ * ========================================================================================= */
+RA_HD void ra_phase5_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) {
+    const unsigned n = s.nSingles;
+    long long K = (long long)pt.G - 1 - s.grantCheck;
+    if (K < 0) K = 0;
+    if ((long long)n <= K) { s.tau = RA_INF32; }
+    else if (K == 0) { s.tau = 0; s.noGrant = 1; }
+    else {
+        ra_u64 prev = 0; bool first = true;
+        for (long long r = 0; r < K; ++r) {
+            ra_u64 best = RA_INF64;
+            for (unsigned j = 0; j < n; ++j) {
+                ra_u64 v = w.singles[j];
+                if ((first || v > prev) && v < best) best = v;
+            }
+            prev = best; first = false;
+        }
+        s.tau = (unsigned)(prev >> 32);
+    }
+    s.grantCheck += (int)n;
+}
+
+RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && idx <= s.tau; }
+
+/* =========================================================================================
+ * Phase 6 -- apply the outcomes of the scans (W:641-648, W:653-661), retire ms T.
+ * items: [0,P) classes, [P, P+nLanders) landers, [.., +nE1) late restarts
+ * ========================================================================================= */
+template <bool DUMP>
+RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, unsigned item) {
+    const RaPointDev& pt = *job.pt;
+    const int T = s.T;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    if (item < (unsigned)pt.P) {
+        const unsigned q = item;
+        const unsigned sq = ra_first_scan(s, q);
+        if (sq != RA_INF32 && sq == s.l1[q] && s.clsSize[q] == 1 && ra_granted(s, sq)) {
+            /* the natural leader is alone and granted: active=2, txTime=T+11, W:642-645 */
+            const size_t at = (size_t)s.l1m[q] * w.cap + s.l1pos[q];
+            uint4 rec = w.bucket[at];
+            w.bucket[at].x = RA_DEAD;
+            s.cnt[s.l1m[q] * pt.P + q] -= 1; s.minIP[s.l1m[q] * pt.P + q] = RA_INF64;
+            if (DUMP) {
+                int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
+                row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
+            }
+            rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
+            ra_msg3_push(w, s, T + 11, rec);
+        }
+        /* the cohort that moved in this ms is gone */
+        s.cnt[((unsigned)T & Rm) * pt.P + q] = 0; s.minIP[((unsigned)T & Rm) * pt.P + q] = RA_INF64;
+        return;
+    }
+    item -= (unsigned)pt.P;
+    if (item < s.nLanders) {
+        uint4 r = w.landerRec[item];
+        const unsigned meta = w.landerMeta[item];
+        if (!(meta & 2u) && ra_granted(s, r.x)) {
+            if (DUMP) { int* row = job.dump + (size_t)r.x * RA_DUMP_W; row[8] = 0; row[9] = (int)ra_rec_mrc(r); }
+            r.y = (unsigned)(T + 11);
+            ra_msg3_push(w, s, T + 11, r);
+        } else {
+            r.y = (unsigned)(T + 1);                        /* txTime++, W:647 / W:658 */
+            ra_schedule(pt, w, s, r);                       /* rarWindow 0 now -> expires at T+Wn */
+        }
+        return;
+    }
+    item -= s.nLanders;
+    if (item < s.nE1) {
+        uint4 r = w.e1Rec[item];
+        if (w.e1Meta[item]) { r.y = (unsigned)(T + 1); ra_schedule(pt, w, s, r); }
+        else ra_park_stale(pt, w, s, T, r);
+    }
+}
+
+RA_HD void ra_phase6_tail(const RaPointDev& pt, RaShared& s) {      /* one thread, after phase 6 */
+    const int T = s.T;
+    s.bcount[(unsigned)T & (unsigned)(pt.R - 1)] = 0;
+    s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
+    s.noGrant = 0;
+    if (s.nSuccess == (unsigned)pt.nUE) { s.done = 1; s.simTime = T; }      /* W:330-334 */
+    else if (T + 1 >= pt.maxTime) { s.done = 1; s.simTime = pt.maxTime; }
+    s.T = T + 1;
+}
+
+/* =========================================================================================
+ * End of the replication (DUMP only): state of the UEs still in flight after the last
+ * executed ms `last`, as the reference's per-ms bookkeeping would have left it.
+ * ========================================================================================= */
+RA_HD void ra_dump_inflight(const RaJob& job, const RaWork& w, RaShared& s, int last, int tid, int nt) {
+    const RaPointDev& pt = *job.pt;
+    for (int slot = 0; slot < pt.R; ++slot) {
+        /* absolute move time of this slot: the value in (last, last+R] congruent to slot */
+        int m = last + 1 + (int)(((unsigned)slot - (unsigned)(last + 1)) & (unsigned)(pt.R - 1));
+        for (unsigned j = tid; j < s.bcount[slot]; j += nt) {
+            uint4 r = w.bucket[(size_t)slot * w.cap + j];
+            if (r.x == RA_DEAD) continue;
+            int* row = job.dump + (size_t)r.x * RA_DUMP_W;
+            int X = (int)r.y;
+            row[0] = last + 1 - (int)ra_rec_ts(r);                         /* timer, W:713 */
+            row[1] = 1;
+            if (ra_rec_flag(r)) {                                          /* stale */
+                int t0 = m - pt.Wn;
+                row[2] = X; row[8] = last - t0; row[5] = X - t0 < 0 ? X - t0 : 0;
+            } else if (X > last) {                                         /* in backoff */
+                row[2] = X; row[8] = 0; row[5] = X - last - 1;
+            } else {                                                       /* transmitted, postponed */
+                row[2] = last + 1; row[8] = last - X + 1; row[5] = 0;
+            }
+            row[6] = (int)ra_rec_p(r); row[7] = 1; row[9] = (int)ra_rec_mrc(r);
+            row[10] = (int)ra_rec_ptc(r); row[11] = 0; row[12] = 0; row[13] = 0;
+            row[14] = (int)ra_rec_fail(r);
+        }
+    }
+    for (int slot = 0; slot < RA_M3RING; ++slot) {
+        for (unsigned j = tid; j < s.m3count[slot]; j += nt) {
+            uint4 r = w.msg3[(size_t)slot * w.cap3 + j];
+            int* row = job.dump + (size_t)r.x * RA_DUMP_W;
+            row[0] = last + 1 - (int)ra_rec_ts(r);
+            row[1] = 2; row[2] = (int)r.y; row[5] = 0; row[6] = (int)ra_rec_p(r); row[7] = 1;
+            row[10] = (int)ra_rec_ptc(r); row[11] = 1; row[12] = ra_rec_flag(r) ? 48 : 0;
+            row[13] = 0; row[14] = (int)ra_rec_fail(r);
+        }
+    }
+}
+
+#endif /* RACH_CORE_CUH */

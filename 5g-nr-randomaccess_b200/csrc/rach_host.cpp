@@ -1,0 +1,121 @@
+/*
+ * rach_host.cpp -- host-side logic of librach_gpu that needs no device: parameter defaults
+ * and validation, the horizon, and the deterministic arrival schedule.
+ *
+ * Reference: RandomAccessWithNOMA.c:69-88 (defaults), :241-255 (horizon, nAccessUE),
+ * :276-292 (arrival gate), :844-847 (beta_dist).  The float/double mix of the reference's
+ * expressions is kept verbatim because ceil() of a float quotient decides integer counts.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rach_gpu.h"
+#include "rach_host.h"
+
+#define betaF 0.0165
+
+/* W:844-847 */
+static float ra_beta_dist(float a, float b, float x) {
+    float betaValue = (1 / betaF) * (pow(x, (a - 1))) * (pow((1 - x), (b - 1)));
+    return betaValue;
+}
+
+extern "C" int ra_params_default(ra_params* p, int variant) {
+    if (!p) return RA_E_INVAL;
+    memset(p, 0, sizeof(*p));
+    p->variant = variant;
+    p->nUE = 10000;
+    p->distribution = 2;            /* W:88 */
+    p->nPreamble = 54;              /* W:71 */
+    p->backoffIndicator = 20;       /* W:72 */
+    p->nGrantUL = 12;               /* W:73 */
+    p->maxRarWindow = 6;            /* W:76 */
+    p->maxMsg2TxCount = 9;          /* W:77 */
+    p->accessTime = 5;              /* W:78 */
+    p->maxTimeMs = 0;
+    p->cellRadius = 400;            /* W:80 */
+    p->hBS = 10.0;                  /* W:81 */
+    p->hUT = 1.8;                   /* W:82 */
+    p->geometry = 1;
+    p->seed = 0;
+    return RA_OK;
+}
+
+extern "C" int ra_horizon_ms(const ra_params* p) {
+    if (!p) return RA_E_INVAL;
+    if (p->maxTimeMs > 0) return p->maxTimeMs;
+    return p->distribution == 1 ? 60000 : 10000;     /* W:243, W:254 */
+}
+
+extern "C" int ra_arrival_schedule(const ra_params* p, int* arrivals, int horizon) {
+    if (!p || !arrivals || horizon < 0 || p->accessTime < 1 || p->nUE < 0) return RA_E_INVAL;
+    const int n = p->nUE, accessTime = p->accessTime;
+    /* the reference's maxTime also scales the Beta shape (time/maxTime, W:285) */
+    const int maxTime = p->distribution == 1 ? 60000 : 10000;
+    int nAccessUE = 0;
+    if (p->distribution == 1) {
+        nAccessUE = ceil((float)n * (float)accessTime * 1.0 / (float)maxTime);   /* W:246 */
+        if (nAccessUE <= 0) nAccessUE = 1;                                         /* W:249-251 */
+    }
+    int activeCheck = 0, allAt = -1;
+    const int nUE = n;
+    for (int time = 0; time < horizon; ++time) {
+        arrivals[time] = 0;
+        if (activeCheck >= nUE) activeCheck = nUE;                                /* W:276-278 */
+        if (time % accessTime == 0 && activeCheck != nUE) {                       /* W:280 */
+            const int before = activeCheck;
+            if (p->distribution == 1) {
+                activeCheck += nAccessUE;
+            } else {
+                float betaDist = ra_beta_dist(3, 4, (float)time / (float)maxTime);
+                int accessUEs = (int)ceil((float)nUE * betaDist / ((float)maxTime / (float)accessTime));
+                activeCheck += accessUEs;
+            }
+            if (activeCheck >= nUE) activeCheck = nUE;                            /* W:290-292 */
+            arrivals[time] = activeCheck - before;
+            if (activeCheck == nUE && allAt < 0) allAt = time;
+        }
+    }
+    return allAt;
+}
+
+static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
+#define RA_BAD(...) do { snprintf(err, errLen, __VA_ARGS__); return RA_E_INVAL; } while (0)
+    if (p->variant != RA_VARIANT_W) RA_BAD("variant %d is not built (only RA_VARIANT_W = W/B dynamics)", p->variant);
+    if (p->nUE < 1 || p->nUE > (1 << 24)) RA_BAD("nUE %d out of range [1, 2^24]", p->nUE);
+    if (p->nPreamble < 1 || p->nPreamble > 256) RA_BAD("nPreamble %d out of range [1, 256]", p->nPreamble);
+    if (p->backoffIndicator < 1 || p->backoffIndicator > 4096) RA_BAD("backoffIndicator %d out of range [1, 4096]", p->backoffIndicator);
+    if (p->nGrantUL < 1) RA_BAD("nGrantUL %d must be >= 1", p->nGrantUL);
+    if (p->maxRarWindow < 2 || p->maxRarWindow > 256) RA_BAD("maxRarWindow %d out of range [2, 256] (RAR window 1..255)", p->maxRarWindow);
+    if (p->maxMsg2TxCount < 0 || p->maxMsg2TxCount > 255) RA_BAD("maxMsg2TxCount %d out of range [0, 255] (max retx 1..256)", p->maxMsg2TxCount);
+    if (p->accessTime < 1 || p->accessTime > 4096) RA_BAD("accessTime %d out of range [1, 4096]", p->accessTime);
+    const int h = ra_horizon_ms(p);
+    if (h < 1 || h > 65535) RA_BAD("horizon %d ms out of range [1, 65535]", h);
+#undef RA_BAD
+    return RA_OK;
+}
+
+int ra_host_ring(const ra_params* p) {
+    const int a = p->accessTime > 5 ? p->accessTime : 5;
+    return next_pow2(p->backoffIndicator + a + p->maxRarWindow + 2);
+}
+
+/* arrCum[occ] = activeCheck after the arrival step of ms occ*accessTime */
+int ra_host_arrcum(const ra_params* p, int* arrCum, int nOcc) {
+    const int h = ra_horizon_ms(p);
+    int* arr = new int[h > 0 ? h : 1];
+    ra_arrival_schedule(p, arr, h);
+    int ac = 0;
+    for (int occ = 0; occ < nOcc; ++occ) {
+        const int t = occ * p->accessTime;
+        if (t < h) ac += arr[t];
+        arrCum[occ] = ac;
+    }
+    delete[] arr;
+    return ac;
+}
+
+extern "C" const char* ra_version(void) { return "rach_b200 0.1 (sm_100a, variant W/B)"; }

@@ -1,0 +1,103 @@
+/*
+ * rach_emu.cpp -- TEST INFRASTRUCTURE.  Runs the phase functions of the CUDA engine
+ * (5g-nr-randomaccess_b200/csrc/rach_core.cuh) on the host, one emulated thread after the
+ * other with the phase boundaries where the kernel has __syncthreads(), so that the
+ * event-driven algorithm can be fuzzed against the oracle without a GPU.  It is NOT a CPU
+ * fallback: nothing in the product loads it, and librach_gpu fails without a device.
+ *
+ * Same ABI as oracle_run()/ref_run() (oracle/ref_api.h).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <vector>
+
+#include "rach_core.cuh"
+#include "rach_gpu.h"
+#include "rach_host.h"
+extern "C" {
+#include "ref_api.h"
+}
+
+template <bool DUMP>
+static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT) {
+    ra_params p; ra_params_default(&p, RA_VARIANT_W);
+    p.nUE = cfg->nUE; p.distribution = cfg->distribution; p.nPreamble = cfg->nPreamble;
+    p.backoffIndicator = cfg->backoffIndicator; p.nGrantUL = cfg->nGrantUL;
+    p.maxRarWindow = cfg->maxRarWindow; p.maxMsg2TxCount = cfg->maxMsg2TxCount;
+    p.accessTime = cfg->accessTime; p.cellRadius = cfg->cellRadius; p.geometry = cfg->geometry;
+    p.seed = cfg->seed; p.maxTimeMs = cfg->stopMs > 0 ? cfg->stopMs : 0;
+    char err[256];
+    if (ra_host_validate(&p, err, sizeof err) != RA_OK) { fprintf(stderr, "emu: %s\n", err); return -1; }
+
+    RaPointDev pt; memset(&pt, 0, sizeof pt);
+    pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
+    pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
+    pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry; pt.R = ra_host_ring(&p);
+    pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed;
+    std::vector<int> arrCum(pt.nOcc);
+    ra_host_arrcum(&p, arrCum.data(), pt.nOcc);
+    pt.arrCum = arrCum.data();
+
+    RaWork w; w.cap = pt.nUE;
+    long long g2 = 2LL * (pt.G < pt.nUE + 1 ? pt.G : pt.nUE + 1) + 2; w.cap3 = (int)g2;
+    std::vector<uint4> bucket((size_t)pt.R * w.cap), msg3((size_t)RA_M3RING * w.cap3), landerRec(w.cap),
+        uncertain(w.cap), c3(w.cap), e1Rec(w.cap3);
+    std::vector<unsigned> landerMeta(w.cap), e1Meta(w.cap3);
+    std::vector<ra_u64> singles(w.cap);
+    w.bucket = bucket.data(); w.msg3 = msg3.data(); w.landerRec = landerRec.data();
+    w.landerMeta = landerMeta.data(); w.uncertain = uncertain.data(); w.c3 = c3.data();
+    w.singles = singles.data(); w.e1Rec = e1Rec.data(); w.e1Meta = e1Meta.data();
+
+    RaShared s; memset(&s, 0, sizeof s);
+    std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8);
+    std::vector<ra_u64> minIP((size_t)pt.R * pt.P);
+    s.cnt = cnt.data(); s.minIP = minIP.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
+    s.N = cls.data(); s.l1 = s.N + pt.P; s.l1pos = s.l1 + pt.P; s.l1m = s.l1pos + pt.P; s.l2 = s.l1m + pt.P;
+    s.before = s.l2 + pt.P; s.extraFirst = s.before + pt.P; s.clsSize = s.extraFirst + pt.P;
+
+    RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
+    std::vector<RaAcc> acc(NT); memset(acc.data(), 0, sizeof(RaAcc) * NT);
+
+    for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
+    while (!s.done) {
+        for (int t = 0; t < NT; ++t) ra_phase0(job, s, t, NT);
+        unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], i);
+        if (s.nC3) ra_phase2_serial(w, s);
+        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, i); }
+        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(w, s, i); }
+        unsigned n4 = (unsigned)pt.P + s.nLanders;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
+        if (s.nSingles) ra_phase5_serial(pt, w, s);
+        unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, i);
+        ra_phase6_tail(pt, s);
+        if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, s.T); return -3; }
+    }
+    const int last = s.simTime < pt.maxTime ? s.simTime : pt.maxTime - 1;
+    if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
+    for (int t = 0; t < NT; ++t) {
+        s.contFailed += acc[t].contFailed; s.collP += acc[t].collP; s.txop += acc[t].txop;
+        s.collScans += acc[t].collScans; s.totScans += acc[t].totScans;
+    }
+    memset(res, 0, sizeof *res);
+    res->simTimeMs = s.simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
+    res->delaySum = (long long)s.delaySum; res->failCountSum = (long long)s.failSum;
+    res->continueFailed = (long long)s.contFailed; res->collisionPreambles = (long long)s.collP;
+    res->totalPreambleTxop = (long long)s.txop; res->collisionScans = (long long)s.collScans;
+    res->totalScans = (long long)s.totScans; res->captured = 1; res->lastMs = last;
+    return 0;
+}
+
+extern "C" int emu_threads = 64;
+
+extern "C" int emu_run(const ref_config* cfg, ref_result* res, int* perUE, float* geom) {
+    (void)geom;
+    struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+    int rc = perUE ? emu_run_t<true>(cfg, res, perUE, emu_threads) : emu_run_t<false>(cfg, res, NULL, emu_threads);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    res->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    return rc;
+}
