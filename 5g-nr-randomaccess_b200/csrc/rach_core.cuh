@@ -92,7 +92,7 @@ struct RaShared {
     unsigned* bcount;         /* [R]   records in each move bucket                          */
     unsigned* m3count;        /* [RA_M3RING]                                                */
     unsigned *N, *l1, *l1pos, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each      */
-    int T, grantCheck, activeCheck, acOld, nArr, done, simTime, overflow;
+    int grantCheck, activeCheck, acOld, nArr, overflow, pad0;
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant;
     ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
@@ -207,7 +207,7 @@ RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
     for (int i = tid; i < RA_M3RING; i += nt) s.m3count[i] = 0;
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
     if (tid == 0) {
-        s.T = 0; s.grantCheck = 0; s.activeCheck = 0; s.done = 0; s.simTime = pt.maxTime; s.overflow = 0;
+        s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0;
         s.nSuccess = 0; s.noGrant = 0;
         s.txSum = s.delaySum = s.failSum = s.contFailed = s.collP = s.txop = s.collScans = s.totScans = 0;
     }
@@ -217,9 +217,9 @@ RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
  * Phase 0 -- start of ms T: grant reset (W:268-269), arrival gate (W:276-292), per-class
  * view of the visible cohorts.
  * ========================================================================================= */
-RA_HD void ra_phase0(const RaJob& job, RaShared& s, int tid, int nt) {
+RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
     const RaPointDev& pt = *job.pt;
-    const int T = s.T, P = pt.P, Wn = pt.Wn;
+    const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1);
     for (int p = tid; p < P; p += nt) {
         unsigned n = 0; ra_u64 best = RA_INF64; unsigned bestm = 0;
@@ -234,7 +234,7 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int tid, int nt) {
     }
     if (tid == 0) {
         if (T % 5 == 0) s.grantCheck = 0;                       /* literal 5, W:268 */
-        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32;
+        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0;
         s.acOld = s.activeCheck;
         if (T % pt.A == 0 && s.activeCheck != pt.nUE) s.activeCheck = pt.arrCum[T / pt.A];
         s.nArr = s.activeCheck - s.acOld;
@@ -250,9 +250,8 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int tid, int nt) {
  *   [.., +nM3)           Msg3 due: requestResourceAllocation, W:667-710
  * ========================================================================================= */
 template <bool DUMP>
-RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
+RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
     const RaPointDev& pt = *job.pt;
-    const int T = s.T;
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < s.nMov) {
         /* ---------------- mover ---------------- */
@@ -392,9 +391,8 @@ RA_HD void ra_phase2_serial(const RaWork& w, RaShared& s) {
  * Phase 3 -- movers below the natural leader of their class, now that s[] is final.
  * ========================================================================================= */
 template <bool DUMP>
-RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, unsigned u) {
+RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned u) {
     const RaPointDev& pt = *job.pt;
-    const int T = s.T;
     const uint4 e = w.uncertain[u];
     const unsigned idx = e.y, p0 = e.z & 0xFFu;
     const unsigned sp = ra_first_scan(s, p0);
@@ -507,9 +505,8 @@ RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && id
  * items: [0,P) classes, [P, P+nLanders) landers, [.., +nE1) late restarts
  * ========================================================================================= */
 template <bool DUMP>
-RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, unsigned item) {
+RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned item) {
     const RaPointDev& pt = *job.pt;
-    const int T = s.T;
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < (unsigned)pt.P) {
         const unsigned q = item;
@@ -527,6 +524,7 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, unsign
             rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
             ra_msg3_push(w, s, T + 11, rec);
         }
+        if (q == 0) { s.bcount[(unsigned)T & Rm] = 0; s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
         /* the cohort that moved in this ms is gone */
         s.cnt[((unsigned)T & Rm) * pt.P + q] = 0; s.minIP[((unsigned)T & Rm) * pt.P + q] = RA_INF64;
         return;
@@ -553,14 +551,11 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, unsign
     }
 }
 
-RA_HD void ra_phase6_tail(const RaPointDev& pt, RaShared& s) {      /* one thread, after phase 6 */
-    const int T = s.T;
-    s.bcount[(unsigned)T & (unsigned)(pt.R - 1)] = 0;
-    s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
-    s.noGrant = 0;
-    if (s.nSuccess == (unsigned)pt.nUE) { s.done = 1; s.simTime = T; }      /* W:330-334 */
-    else if (T + 1 >= pt.maxTime) { s.done = 1; s.simTime = pt.maxTime; }
-    s.T = T + 1;
+/* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */
+RA_HD bool ra_ms_done(const RaPointDev& pt, const RaShared& s, int T, int* simTime) {
+    if (s.nSuccess == (unsigned)pt.nUE) { *simTime = T; return true; }
+    if (T + 1 >= pt.maxTime) { *simTime = pt.maxTime; return true; }
+    return false;
 }
 
 /* =========================================================================================

@@ -1,0 +1,482 @@
+/*
+ * rach_engine.cu -- librach_gpu: the CUDA (sm_100a) step kernel and the C ABI of
+ * include/rach_gpu.h.
+ *
+ * One thread block simulates one replication from ms 0 to the horizon: it owns the move /
+ * Msg3 calendars of that replication in HBM (16-byte records, 128-bit loads and stores) and
+ * the per-preamble cohort tables in shared memory, and runs the phases of rach_core.cuh with
+ * __syncthreads() in between.  Blocks are persistent: grid = min(jobs, SMs * CTAs/SM) and
+ * each block pulls replications from an atomic job counter.  Replications never exchange
+ * data, so multi-GPU is a partition of the job list (no collective in the data path).
+ *
+ * Replaces the body of the reference's (seed, nUE) loop, RandomAccessWithNOMA.c:229-368.
+ * There is no CPU path in this library.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "rach_core.cuh"
+#include "rach_gpu.h"
+#include "rach_host.h"
+
+#define RA_NT 256          /* threads per block */
+
+struct RaKernelArgs {
+    const RaPointDev* points;
+    const int*        jobPoint;     /* [nJobs] point index                       */
+    const unsigned*   jobRep;       /* [nJobs] tape replication id               */
+    const RaWork*     works;        /* [gridDim.x]                               */
+    unsigned*         jobCounter;
+    ra_stats*         stats;        /* [nJobs]                                   */
+    int*              dump;         /* [nJobs][dumpStride] or NULL               */
+    int*              errFlag;
+    size_t            dumpStride;
+    int               nJobs, maxP, maxR;
+};
+
+__device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R, int P) {
+    s.minIP = reinterpret_cast<ra_u64*>(base);                 base += sizeof(ra_u64) * (size_t)R * P;
+    s.cnt = reinterpret_cast<unsigned*>(base);                 base += sizeof(unsigned) * (size_t)R * P;
+    s.bcount = reinterpret_cast<unsigned*>(base);              base += sizeof(unsigned) * (size_t)R;
+    s.m3count = reinterpret_cast<unsigned*>(base);             base += sizeof(unsigned) * RA_M3RING;
+    unsigned* c = reinterpret_cast<unsigned*>(base);
+    s.N = c; s.l1 = c + P; s.l1pos = c + 2 * P; s.l1m = c + 3 * P; s.l2 = c + 4 * P;
+    s.before = c + 5 * P; s.extraFirst = c + 6 * P; s.clsSize = c + 7 * P;
+}
+
+static size_t ra_smem_bytes(int R, int P) {
+    return sizeof(ra_u64) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
+           sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P;
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(RA_NT) ra_step_kernel(RaKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
+    __shared__ RaShared s;
+    __shared__ RaPointDev sPt;
+    __shared__ int sJob;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const RaWork w = a.works[blockIdx.x];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sJob = (int)atomicAdd(a.jobCounter, 1u);
+        __syncthreads();
+        const int jobId = sJob;
+        if (jobId >= a.nJobs) break;
+        if (tid == 0) {
+            sPt = a.points[a.jobPoint[jobId]];
+            ra_carve(s, ra_dyn_smem, sPt.R, sPt.P);
+        }
+        __syncthreads();
+        const RaPointDev& pt = sPt;
+        RaJob job; job.pt = &pt; job.rep = a.jobRep[jobId];
+        job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
+        ra_job_init<DUMP>(job, s, tid, nt);
+        RaAcc acc; acc.contFailed = acc.collP = acc.txop = acc.collScans = acc.totScans = 0;
+        __syncthreads();
+
+        int simTime = pt.maxTime;
+        for (int T = 0;; ++T) {
+            ra_phase0(job, s, T, tid, nt);
+            __syncthreads();
+            {
+                const unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
+                for (unsigned i = tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
+            }
+            __syncthreads();
+            if (s.nC3) {
+                if (tid == 0) ra_phase2_serial(w, s);
+                __syncthreads();
+            }
+            if (s.nUnc) {
+                const unsigned n = s.nUnc;
+                for (unsigned i = tid; i < n; i += nt) ra_phase3_item<DUMP>(job, w, s, T, i);
+                __syncthreads();
+            }
+            if (s.nE1) {
+                const unsigned n = s.nE1;
+                for (unsigned i = tid; i < n; i += nt) ra_phase3b_item(w, s, i);
+                __syncthreads();
+            }
+            {
+                const unsigned n4 = (unsigned)pt.P + s.nLanders;
+                for (unsigned i = tid; i < n4; i += nt) ra_phase4_item(pt, w, s, acc, i);
+            }
+            __syncthreads();
+            if (s.nSingles) {
+                if (tid == 0) ra_phase5_serial(pt, w, s);
+                __syncthreads();
+            }
+            {
+                const unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
+                for (unsigned i = tid; i < n6; i += nt) ra_phase6_item<DUMP>(job, w, s, T, i);
+            }
+            __syncthreads();
+            if (ra_ms_done(pt, s, T, &simTime)) break;
+        }
+        const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
+        if (DUMP) ra_dump_inflight(job, w, s, last, tid, nt);
+        if (acc.contFailed) atomicAdd(&s.contFailed, (ra_u64)acc.contFailed);
+        if (acc.collP) atomicAdd(&s.collP, (ra_u64)acc.collP);
+        if (acc.txop) atomicAdd(&s.txop, (ra_u64)acc.txop);
+        if (acc.collScans) atomicAdd(&s.collScans, (ra_u64)acc.collScans);
+        if (acc.totScans) atomicAdd(&s.totScans, (ra_u64)acc.totScans);
+        __syncthreads();
+        if (tid == 0) {
+            ra_stats st;
+            st.simTimeMs = simTime; st.nSuccess = (int)s.nSuccess;
+            st.preambleTxSum = (long long)s.txSum; st.delaySum = (long long)s.delaySum;
+            st.failCountSum = (long long)s.failSum; st.continueFailed = (long long)s.contFailed;
+            st.finalSuccess = (long long)s.nSuccess;                 /* W:676: one per success */
+            st.collisionPreambles = (long long)s.collP; st.totalPreambleTxop = (long long)s.txop;
+            st.collisionScans = (long long)s.collScans; st.totalScans = (long long)s.totScans;
+            st.updates = (long long)pt.nUE * (long long)((simTime + pt.A - 1) / pt.A);
+            a.stats[jobId] = st;
+            if (s.overflow) atomicExch(a.errFlag, s.overflow);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * activateUEs side outputs, RandomAccessWithNOMA.c:392-415, recomputed from the draw tape.
+ * Types follow the C semantics of the reference: float locals, double libm calls.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void ra_geometry_kernel(RaPointDev pt, unsigned rep, int lastArrivalMs, float cellRadius, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pt.nUE) return;
+    float* o = out + (size_t)i * 6;
+    /* arrival ms: first occasion whose cumulative count exceeds i */
+    int lo = 0, hi = pt.nOcc;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (pt.arrCum[mid] > i) hi = mid; else lo = mid + 1; }
+    const int time = lo * pt.A;
+    if (lo >= pt.nOcc || time > lastArrivalMs) { for (int k = 0; k < 6; ++k) o[k] = 0.f; return; }
+    rach_u32x4 d = rach_tape_block(pt.seed, rep, (unsigned)i, (unsigned)time, 0u, RACH_TAPE_TAG_UE);
+    const float bandwidth = 5;                                                    /* W:64 */
+    float pi = 3.14;
+    float theta = (float)(int)(d.v[0] >> 1) / (float)(2147483647) * 2 * pi;      /* W:393 */
+    float r = (float)((double)cellRadius * sqrt((double)((float)(int)(d.v[1] >> 1) / (float)2147483647)));   /* W:394 */
+    int sector = ra_sector((int)(d.v[0] >> 1));
+    o[0] = theta;
+    o[1] = (float)((double)r * cos((double)theta));                              /* W:412 */
+    o[2] = (float)((double)r * sin((double)theta));                              /* W:413 */
+    o[3] = r;                                                                    /* W:414 */
+    o[4] = (float)(20 * log10(4. * (double)pi * (double)r / (double)(bandwidth / 1000)));   /* W:415 */
+    o[5] = (float)sector;
+}
+
+/* ========================================================================================== */
+/*                                        host side                                           */
+/* ========================================================================================== */
+struct RaDev {
+    int id = 0;
+    std::vector<int> jobs;            /* global job ids run on this device */
+    RaPointDev* dPoints = nullptr;
+    std::vector<int*> dArrCum;
+    int* dJobPoint = nullptr; unsigned* dJobRep = nullptr; unsigned* dCounter = nullptr;
+    ra_stats* dStats = nullptr; RaWork* dWorks = nullptr; unsigned char* dWorkspace = nullptr;
+    int* dDump = nullptr; int* dErr = nullptr; float* dGeom = nullptr;
+    int grid = 0; size_t smem = 0;
+    cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<ra_stats> hStats;
+};
+
+struct ra_sim {
+    std::vector<ra_params> points;
+    std::vector<RaPointDev> hostPoints;       /* arrCum unset; per-device copies carry the pointers */
+    std::vector<std::vector<int>> arrCum;
+    int nPoints = 0, reps = 0;
+    ra_options opt;
+    std::vector<RaDev> devs;
+    std::vector<ra_stats> stats;              /* [nPoints*reps] */
+    std::vector<int> jobDev, jobLocal;        /* where each global job ran */
+    bool ran = false;
+    double kernelMs = 0; long long launches = 0;
+    size_t dumpStride = 0;
+    int maxP = 0, maxR = 0, cap = 0, cap3 = 0;
+    std::string err;
+};
+
+static thread_local std::string g_createErr;
+
+#define RA_CUDA(sim, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    (sim)->err = b_; return RA_E_CUDA; } } while (0)
+
+static void ra_free_dev(RaDev& d) {
+    cudaSetDevice(d.id);
+    for (int* p : d.dArrCum) cudaFree(p);
+    cudaFree(d.dPoints); cudaFree(d.dJobPoint); cudaFree(d.dJobRep); cudaFree(d.dCounter);
+    cudaFree(d.dStats); cudaFree(d.dWorks); cudaFree(d.dWorkspace); cudaFree(d.dDump); cudaFree(d.dErr);
+    cudaFree(d.dGeom);
+    if (d.e0) cudaEventDestroy(d.e0);
+    if (d.e1) cudaEventDestroy(d.e1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+}
+
+static size_t ra_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int ra_setup_device(ra_sim* sim, RaDev& d) {
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    cudaDeviceProp prop;
+    RA_CUDA(sim, cudaGetDeviceProperties(&prop, d.id));
+    RA_CUDA(sim, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    RA_CUDA(sim, cudaEventCreate(&d.e0));
+    RA_CUDA(sim, cudaEventCreate(&d.e1));
+    const int nJobs = (int)d.jobs.size();
+
+    /* points + arrival tables */
+    std::vector<RaPointDev> pts = sim->hostPoints;
+    d.dArrCum.resize(sim->nPoints, nullptr);
+    for (int i = 0; i < sim->nPoints; ++i) {
+        RA_CUDA(sim, cudaMalloc(&d.dArrCum[i], sizeof(int) * sim->arrCum[i].size()));
+        RA_CUDA(sim, cudaMemcpy(d.dArrCum[i], sim->arrCum[i].data(), sizeof(int) * sim->arrCum[i].size(), cudaMemcpyHostToDevice));
+        pts[i].arrCum = d.dArrCum[i];
+    }
+    RA_CUDA(sim, cudaMalloc(&d.dPoints, sizeof(RaPointDev) * pts.size()));
+    RA_CUDA(sim, cudaMemcpy(d.dPoints, pts.data(), sizeof(RaPointDev) * pts.size(), cudaMemcpyHostToDevice));
+
+    /* job list */
+    std::vector<int> jp(nJobs); std::vector<unsigned> jr(nJobs);
+    for (int j = 0; j < nJobs; ++j) {
+        jp[j] = d.jobs[j] / sim->reps;
+        jr[j] = (unsigned)(sim->opt.repOffset + d.jobs[j] % sim->reps);
+    }
+    RA_CUDA(sim, cudaMalloc(&d.dJobPoint, sizeof(int) * std::max(nJobs, 1)));
+    RA_CUDA(sim, cudaMalloc(&d.dJobRep, sizeof(unsigned) * std::max(nJobs, 1)));
+    RA_CUDA(sim, cudaMemcpy(d.dJobPoint, jp.data(), sizeof(int) * nJobs, cudaMemcpyHostToDevice));
+    RA_CUDA(sim, cudaMemcpy(d.dJobRep, jr.data(), sizeof(unsigned) * nJobs, cudaMemcpyHostToDevice));
+    RA_CUDA(sim, cudaMalloc(&d.dCounter, sizeof(unsigned)));
+    RA_CUDA(sim, cudaMalloc(&d.dErr, sizeof(int)));
+    RA_CUDA(sim, cudaMalloc(&d.dStats, sizeof(ra_stats) * std::max(nJobs, 1)));
+    d.hStats.resize(nJobs);
+    if (sim->opt.dumpUEs) {
+        size_t bytes = sizeof(int) * sim->dumpStride * (size_t)std::max(nJobs, 1);
+        cudaError_t e = cudaMalloc(&d.dDump, bytes);
+        if (e != cudaSuccess) { sim->err = "dump buffer does not fit on the device (dumpUEs keeps nUE*16 ints per replication)"; return RA_E_NOMEM; }
+    }
+
+    /* grid and per-block workspace */
+    d.smem = ra_smem_bytes(sim->maxR, sim->maxP);
+    if (d.smem > (size_t)prop.sharedMemPerBlockOptin) {
+        sim->err = "cohort tables (ring x preambles) exceed the shared memory of one block"; return RA_E_INVAL;
+    }
+    if (sim->opt.dumpUEs) RA_CUDA(sim, cudaFuncSetAttribute(ra_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
+    else RA_CUDA(sim, cudaFuncSetAttribute(ra_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
+    int occ = 0;
+    if (sim->opt.dumpUEs) RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<true>, RA_NT, d.smem));
+    else RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<false>, RA_NT, d.smem));
+    if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
+    int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, 4);
+
+    const size_t cap = (size_t)sim->cap, cap3 = (size_t)sim->cap3;
+    size_t off = 0;
+    const size_t oBucket = off;    off = ra_align_up(off + sizeof(uint4) * cap * sim->maxR, 256);
+    const size_t oMsg3 = off;      off = ra_align_up(off + sizeof(uint4) * cap3 * RA_M3RING, 256);
+    const size_t oLander = off;    off = ra_align_up(off + sizeof(uint4) * cap, 256);
+    const size_t oLMeta = off;     off = ra_align_up(off + sizeof(unsigned) * cap, 256);
+    const size_t oUnc = off;       off = ra_align_up(off + sizeof(uint4) * cap, 256);
+    const size_t oC3 = off;        off = ra_align_up(off + sizeof(uint4) * cap, 256);
+    const size_t oSingles = off;   off = ra_align_up(off + sizeof(ra_u64) * cap, 256);
+    const size_t oE1 = off;        off = ra_align_up(off + sizeof(uint4) * cap3, 256);
+    const size_t oE1Meta = off;    off = ra_align_up(off + sizeof(unsigned) * cap3, 256);
+    const size_t perBlock = off;
+
+    size_t freeB = 0, totalB = 0;
+    RA_CUDA(sim, cudaMemGetInfo(&freeB, &totalB));
+    size_t budget = (size_t)((double)freeB * 0.85);
+    int grid = std::min(nJobs, prop.multiProcessorCount * perSM);
+    if ((size_t)grid * perBlock > budget) grid = (int)(budget / perBlock);
+    if (grid < 1) { sim->err = "not enough device memory for one replication workspace"; return RA_E_NOMEM; }
+    d.grid = grid;
+    {
+        cudaError_t e = cudaMalloc(&d.dWorkspace, perBlock * (size_t)grid);
+        if (e != cudaSuccess) { sim->err = std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e); return RA_E_NOMEM; }
+    }
+    std::vector<RaWork> works(grid);
+    for (int b = 0; b < grid; ++b) {
+        unsigned char* base = d.dWorkspace + perBlock * (size_t)b;
+        RaWork& w = works[b];
+        w.bucket = (uint4*)(base + oBucket); w.msg3 = (uint4*)(base + oMsg3);
+        w.landerRec = (uint4*)(base + oLander); w.landerMeta = (unsigned*)(base + oLMeta);
+        w.uncertain = (uint4*)(base + oUnc); w.c3 = (uint4*)(base + oC3);
+        w.singles = (ra_u64*)(base + oSingles); w.e1Rec = (uint4*)(base + oE1);
+        w.e1Meta = (unsigned*)(base + oE1Meta); w.cap = sim->cap; w.cap3 = sim->cap3;
+    }
+    RA_CUDA(sim, cudaMalloc(&d.dWorks, sizeof(RaWork) * grid));
+    RA_CUDA(sim, cudaMemcpy(d.dWorks, works.data(), sizeof(RaWork) * grid, cudaMemcpyHostToDevice));
+    return RA_OK;
+}
+
+extern "C" const char* ra_last_create_error(void) { return g_createErr.c_str(); }
+
+extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int repsPerPoint,
+                                    const int* devices, int nDevices, const ra_options* opt) {
+    g_createErr.clear();
+    if (!points || nPoints < 1 || repsPerPoint < 1) { g_createErr = "points/nPoints/repsPerPoint invalid"; return nullptr; }
+    int devCount = 0;
+    if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount < 1) {
+        g_createErr = "no CUDA device: librach_gpu has no CPU path"; return nullptr;
+    }
+    ra_sim* sim = new ra_sim();
+    memset(&sim->opt, 0, sizeof sim->opt);
+    if (opt) sim->opt = *opt;
+    sim->nPoints = nPoints; sim->reps = repsPerPoint;
+    sim->points.assign(points, points + nPoints);
+    char err[256];
+    for (int i = 0; i < nPoints; ++i) {
+        if (ra_host_validate(&points[i], err, sizeof err) != RA_OK) {
+            g_createErr = std::string("point ") + std::to_string(i) + ": " + err; delete sim; return nullptr;
+        }
+        const ra_params& p = points[i];
+        RaPointDev pt; memset(&pt, 0, sizeof pt);
+        pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
+        pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
+        pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry ? 1 : 0; pt.R = ra_host_ring(&p);
+        pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.arrCum = nullptr;
+        sim->hostPoints.push_back(pt);
+        sim->arrCum.emplace_back(pt.nOcc);
+        ra_host_arrcum(&p, sim->arrCum.back().data(), pt.nOcc);
+        sim->maxP = std::max(sim->maxP, pt.P); sim->maxR = std::max(sim->maxR, pt.R);
+        sim->cap = std::max(sim->cap, pt.nUE);
+        long long g2 = 2LL * std::min<long long>(pt.G, (long long)pt.nUE + 1) + 2;
+        sim->cap3 = std::max<long long>(sim->cap3, g2);
+        sim->dumpStride = std::max(sim->dumpStride, (size_t)pt.nUE * RA_DUMP_W);
+    }
+    std::vector<int> devs;
+    if (!devices || nDevices < 1) devs.push_back(0);
+    else devs.assign(devices, devices + nDevices);
+    for (int dv : devs) if (dv < 0 || dv >= devCount) { g_createErr = "device index out of range"; delete sim; return nullptr; }
+
+    /* longest replications first, dealt round-robin to the devices */
+    const int nJobs = nPoints * repsPerPoint;
+    std::vector<int> order(nJobs);
+    for (int j = 0; j < nJobs; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const RaPointDev& pa = sim->hostPoints[a / repsPerPoint]; const RaPointDev& pb = sim->hostPoints[b / repsPerPoint];
+        return (long long)pa.nUE * pa.maxTime > (long long)pb.nUE * pb.maxTime; });
+    sim->devs.resize(devs.size());
+    sim->jobDev.resize(nJobs); sim->jobLocal.resize(nJobs);
+    for (size_t k = 0; k < devs.size(); ++k) sim->devs[k].id = devs[k];
+    for (int k = 0; k < nJobs; ++k) {
+        RaDev& d = sim->devs[k % devs.size()];
+        sim->jobDev[order[k]] = (int)(k % devs.size()); sim->jobLocal[order[k]] = (int)d.jobs.size();
+        d.jobs.push_back(order[k]);
+    }
+    sim->stats.resize(nJobs);
+    for (RaDev& d : sim->devs) {
+        int rc = ra_setup_device(sim, d);
+        if (rc != RA_OK) { g_createErr = sim->err; ra_sim_destroy(sim); return nullptr; }
+    }
+    return sim;
+}
+
+extern "C" ra_sim* ra_sim_create(const ra_params* points, int nPoints, int repsPerPoint,
+                                 const int* devices, int nDevices) {
+    return ra_sim_create_ex(points, nPoints, repsPerPoint, devices, nDevices, nullptr);
+}
+
+extern "C" int ra_sim_run(ra_sim* sim) {
+    if (!sim) return RA_E_INVAL;
+    sim->launches = 0;
+    for (RaDev& d : sim->devs) {
+        const int nJobs = (int)d.jobs.size();
+        if (!nJobs) continue;
+        RA_CUDA(sim, cudaSetDevice(d.id));
+        RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
+        RA_CUDA(sim, cudaMemsetAsync(d.dErr, 0, sizeof(int), d.stream));
+        RaKernelArgs a;
+        a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
+        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr;
+        a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
+        RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
+        if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+        else ra_step_kernel<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+        RA_CUDA(sim, cudaGetLastError());
+        RA_CUDA(sim, cudaEventRecord(d.e1, d.stream));
+        RA_CUDA(sim, cudaMemcpyAsync(d.hStats.data(), d.dStats, sizeof(ra_stats) * nJobs, cudaMemcpyDeviceToHost, d.stream));
+        sim->launches++;
+    }
+    double ms = 0;
+    for (RaDev& d : sim->devs) {
+        if (d.jobs.empty()) continue;
+        RA_CUDA(sim, cudaSetDevice(d.id));
+        RA_CUDA(sim, cudaStreamSynchronize(d.stream));
+        float t = 0; RA_CUDA(sim, cudaEventElapsedTime(&t, d.e0, d.e1));
+        ms = std::max(ms, (double)t);
+        int flag = 0;
+        RA_CUDA(sim, cudaMemcpy(&flag, d.dErr, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) {
+            sim->err = flag == 1 ? "engine self-check: a calendar bucket overflowed" : "engine self-check: a packed per-UE counter overflowed (preambleTxCounter > 32767, failCount > 65535)";
+            return RA_E_INTERNAL;
+        }
+        for (size_t j = 0; j < d.jobs.size(); ++j) sim->stats[d.jobs[j]] = d.hStats[j];
+    }
+    sim->kernelMs = ms; sim->ran = true;
+    return RA_OK;
+}
+
+extern "C" int ra_sim_stats(ra_sim* sim, int point, int rep, ra_stats* out) {
+    if (!sim || !out) return RA_E_INVAL;
+    if (!sim->ran) { sim->err = "ra_sim_stats before ra_sim_run"; return RA_E_STATE; }
+    if (point < 0 || point >= sim->nPoints || rep < 0 || rep >= sim->reps) { sim->err = "point/rep out of range"; return RA_E_INVAL; }
+    *out = sim->stats[(size_t)point * sim->reps + rep];
+    return RA_OK;
+}
+
+extern "C" int ra_sim_stats_all(ra_sim* sim, ra_stats* out) {
+    if (!sim || !out) return RA_E_INVAL;
+    if (!sim->ran) { sim->err = "ra_sim_stats_all before ra_sim_run"; return RA_E_STATE; }
+    memcpy(out, sim->stats.data(), sizeof(ra_stats) * sim->stats.size());
+    return RA_OK;
+}
+
+extern "C" int ra_sim_dump_ues(ra_sim* sim, int point, int rep, int* out) {
+    if (!sim || !out) return RA_E_INVAL;
+    if (!sim->ran) { sim->err = "ra_sim_dump_ues before ra_sim_run"; return RA_E_STATE; }
+    if (!sim->opt.dumpUEs) { sim->err = "ra_sim_dump_ues needs ra_options.dumpUEs = 1 at create time"; return RA_E_STATE; }
+    if (point < 0 || point >= sim->nPoints || rep < 0 || rep >= sim->reps) { sim->err = "point/rep out of range"; return RA_E_INVAL; }
+    const int job = point * sim->reps + rep;
+    RaDev& d = sim->devs[sim->jobDev[job]];
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    RA_CUDA(sim, cudaMemcpy(out, d.dDump + (size_t)sim->jobLocal[job] * sim->dumpStride,
+                            sizeof(int) * (size_t)sim->points[point].nUE * RA_DUMP_W, cudaMemcpyDeviceToHost));
+    return RA_OK;
+}
+
+extern "C" int ra_sim_geometry(ra_sim* sim, int point, int rep, float* out) {
+    if (!sim || !out) return RA_E_INVAL;
+    if (!sim->ran) { sim->err = "ra_sim_geometry before ra_sim_run"; return RA_E_STATE; }
+    if (point < 0 || point >= sim->nPoints || rep < 0 || rep >= sim->reps) { sim->err = "point/rep out of range"; return RA_E_INVAL; }
+    if (!sim->points[point].geometry) { sim->err = "ra_sim_geometry needs geometry = 1 (variant B draws no positions)"; return RA_E_STATE; }
+    RaDev& d = sim->devs[0];
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    const int n = sim->points[point].nUE;
+    if (!d.dGeom) RA_CUDA(sim, cudaMalloc(&d.dGeom, sizeof(float) * 6 * (size_t)sim->cap));
+    RaPointDev pt = sim->hostPoints[point]; pt.arrCum = d.dArrCum[point];
+    /* UEs arrive only in ms the loop executed: up to simTime (break ms) or horizon-1 */
+    const ra_stats& st = sim->stats[(size_t)point * sim->reps + rep];
+    const int lastMs = st.simTimeMs < pt.maxTime ? st.simTimeMs : pt.maxTime - 1;
+    ra_geometry_kernel<<<(n + 255) / 256, 256, 0, d.stream>>>(pt, (unsigned)(sim->opt.repOffset + rep), lastMs,
+                                                               sim->points[point].cellRadius, d.dGeom);
+    RA_CUDA(sim, cudaGetLastError());
+    RA_CUDA(sim, cudaMemcpyAsync(out, d.dGeom, sizeof(float) * 6 * (size_t)n, cudaMemcpyDeviceToHost, d.stream));
+    RA_CUDA(sim, cudaStreamSynchronize(d.stream));
+    return RA_OK;
+}
+
+extern "C" double ra_sim_kernel_ms(const ra_sim* sim) { return sim ? sim->kernelMs : 0.0; }
+extern "C" long long ra_sim_gpu_launches(const ra_sim* sim) { return sim ? sim->launches : 0; }
+extern "C" const char* ra_sim_last_error(const ra_sim* sim) { return sim ? sim->err.c_str() : "null handle"; }
+
+extern "C" void ra_sim_destroy(ra_sim* sim) {
+    if (!sim) return;
+    for (RaDev& d : sim->devs) ra_free_dev(d);
+    delete sim;
+}

@@ -61,29 +61,30 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     std::vector<RaAcc> acc(NT); memset(acc.data(), 0, sizeof(RaAcc) * NT);
 
     for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
-    while (!s.done) {
-        for (int t = 0; t < NT; ++t) ra_phase0(job, s, t, NT);
+    int simTime = pt.maxTime;
+    for (int T = 0;; ++T) {
+        for (int t = 0; t < NT; ++t) ra_phase0(job, s, T, t, NT);
         unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], i);
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
         if (s.nC3) ra_phase2_serial(w, s);
-        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, i); }
+        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
         if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(w, s, i); }
         unsigned n4 = (unsigned)pt.P + s.nLanders;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
         if (s.nSingles) ra_phase5_serial(pt, w, s);
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, i);
-        ra_phase6_tail(pt, s);
-        if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, s.T); return -3; }
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
+        if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
+        if (ra_ms_done(pt, s, T, &simTime)) break;
     }
-    const int last = s.simTime < pt.maxTime ? s.simTime : pt.maxTime - 1;
+    const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
     if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
     for (int t = 0; t < NT; ++t) {
         s.contFailed += acc[t].contFailed; s.collP += acc[t].collP; s.txop += acc[t].txop;
         s.collScans += acc[t].collScans; s.totScans += acc[t].totScans;
     }
     memset(res, 0, sizeof *res);
-    res->simTimeMs = s.simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
+    res->simTimeMs = simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
     res->delaySum = (long long)s.delaySum; res->failCountSum = (long long)s.failSum;
     res->continueFailed = (long long)s.contFailed; res->collisionPreambles = (long long)s.collP;
     res->totalPreambleTxop = (long long)s.txop; res->collisionScans = (long long)s.collScans;
@@ -91,7 +92,7 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     return 0;
 }
 
-extern "C" int emu_threads = 64;
+extern "C" { int emu_threads = 64; }
 
 extern "C" int emu_run(const ref_config* cfg, ref_result* res, int* perUE, float* geom) {
     (void)geom;

@@ -1,0 +1,72 @@
+"""The CUDA engine's phase functions (5g-nr-randomaccess_b200/csrc/rach_core.cuh) compiled for the
+host (tests/emu) and run thread by thread, against the oracle restatement and the reference
+fixtures.  Proves the event-driven formulation exact on CPU; the -m gpu tests prove the kernel."""
+import ctypes as C
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ["simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "failCountSum", "continueFailed",
+        "collisionPreambles", "totalPreambleTxop", "collisionScans", "totalScans"]
+
+
+@pytest.fixture(scope="module")
+def emu(oracle):
+    so = subprocess.check_output([os.path.join(ROOT, "tests", "emu", "build_emu.sh")]).decode().strip()
+    f = oracle._lib(so, "emu_run")
+    thr = C.c_int.in_dll(C.CDLL(so), "emu_threads")
+    return f, thr
+
+
+def _cmp(oracle, emu, kw, threads=64):
+    f, thr = emu
+    thr.value = threads
+    cfg = oracle.make_config(**kw)
+    p, ue, _ = oracle.run_port(cfg)
+    e, ue2, _ = oracle._run(f, cfg, True, False)
+    for k in KEYS:
+        assert getattr(p, k) == getattr(e, k), (k, kw)
+    np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+    return p
+
+
+def test_defaults(oracle, emu):
+    _cmp(oracle, emu, dict(nUE=10000, seed=1, rep=2))
+    _cmp(oracle, emu, dict(nUE=20000, seed=5), threads=256)
+
+
+def test_against_reference_fixtures(oracle, emu, golden):
+    stats, _ = golden
+    f, thr = emu
+    thr.value = 128
+    for name, g in stats.items():
+        if g["variant"] != "w" or g["config"]["nUE"] > 10000:
+            continue
+        cfg = oracle.make_config(**g["config"])
+        e, ue, _ = oracle._run(f, cfg, True, False)
+        for k in KEYS[:8]:
+            assert getattr(e, k) == g["stats"][k], (name, k)
+        assert hashlib.sha256(np.ascontiguousarray(ue).tobytes()).hexdigest() == g["ue_sha256"], name
+
+
+def test_fuzz(oracle, emu):
+    rnd = random.Random(77)
+    late = 0
+    for _ in range(60):
+        kw = dict(nUE=rnd.choice([1, 2, 7, 50, 300, 1500, 4000]),
+                  distribution=rnd.choice([1, 2, 2, 2]),
+                  nPreamble=rnd.choice([1, 2, 3, 8, 54, 64]),
+                  backoffIndicator=rnd.choice([1, 2, 5, 20, 40]),
+                  nGrantUL=rnd.choice([1, 2, 4, 12, 54]),
+                  maxRarWindow=rnd.choice([2, 3, 6, 6, 9]),
+                  maxMsg2TxCount=rnd.choice([0, 1, 3, 9, 19]),
+                  accessTime=rnd.choice([1, 2, 3, 5, 5, 5, 6, 7, 10]),
+                  seed=rnd.getrandbits(64), rep=rnd.randrange(5000),
+                  geometry=rnd.choice([0, 1]), stopMs=rnd.choice([0, 0, 0, 777, 3001]))
+        late += _cmp(oracle, emu, kw, threads=rnd.choice([1, 3, 32, 64, 256])).lateAbsorbed
+    assert late > 0
