@@ -53,7 +53,7 @@ class RaOptions(C.Structure):
 
 SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_sim_run", "ra_sim_stats",
            "ra_sim_stats_all", "ra_sim_dump_ues", "ra_sim_geometry", "ra_sim_kernel_ms",
-           "ra_sim_gpu_launches", "ra_sim_destroy", "ra_sim_last_error", "ra_params_default",
+           "ra_sim_gpu_launches", "ra_sim_phase_cycles", "ra_sim_destroy", "ra_sim_last_error", "ra_params_default",
            "ra_horizon_ms", "ra_arrival_schedule", "ra_version"]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_lib():
     lib.ra_sim_kernel_ms.argtypes = [vp]
     lib.ra_sim_gpu_launches.restype = C.c_longlong
     lib.ra_sim_gpu_launches.argtypes = [vp]
+    lib.ra_sim_phase_cycles.argtypes = [vp, vp]
     lib.ra_sim_destroy.argtypes = [vp]
     lib.ra_sim_destroy.restype = None
     lib.ra_sim_last_error.restype = C.c_char_p
@@ -165,6 +166,11 @@ class RachSim:
         n = self.points[point].nUE
         out = np.zeros((n, 6), dtype=np.float32)
         self._check(self._lib.ra_sim_geometry(self._h, point, rep, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def phase_cycles(self):
+        out = np.zeros(10, dtype=np.uint64)
+        self._check(self._lib.ra_sim_phase_cycles(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
     @property

@@ -51,6 +51,9 @@ typedef unsigned long long ra_u64;
 #define RA_DEAD  0xFFFFFFFFu
 #define RA_M3RING 64
 #define RA_DUMP_W 16
+#define RA_HBINS 1024       /* histogram bins of the grant selection            */
+#define RA_SCAP  2048       /* singleton scans of one ms kept in shared memory  */
+#define RA_MAGIC5 858993460u /* ra_magic(5) */
 
 /* ---- atomics: CUDA on the device, plain read-modify-write in the host emulator ---------- */
 #ifdef __CUDA_ARCH__
@@ -66,7 +69,8 @@ template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) 
 /* ---- one parameter point, device view ---------------------------------------------------- */
 struct RaPointDev {
     int nUE, P, BI, G, Wn, M, A, maxTime;
-    int geometry, R, nOcc, pad;
+    int geometry, R, nOcc, hshift;  /* hshift: idx >> hshift < RA_HBINS */
+    unsigned magicBI, magicP, magicA, pad; /* ra_magic() of the three runtime divisors */
     ra_u64 seed;
     const int* arrCum;        /* [nOcc] activeCheck after the arrival step of ms occ*A (W:280-292) */
 };
@@ -79,7 +83,7 @@ struct RaWork {
     unsigned* landerMeta;     /* [cap]  bit0: member of its class at start of ms; bits 8..: late joins */
     uint4*    uncertain;      /* [cap]  movers below the natural leader: pos, idx, p0|limit<<31 */
     uint4*    c3;             /* [cap]  limit movers that land iff not postponed: idx,p0,pnew,landed */
-    ra_u64*   singles;        /* [cap]  singleton scans of the ms: idx<<32 | ref            */
+    unsigned* singles;        /* [cap]  UE index of every singleton scan of the ms          */
     uint4*    e1Rec;          /* [cap3] Msg3 restarts that land on the current ms (W:693)   */
     unsigned* e1Meta;         /* [cap3] 1 = absorbed by a later scan                        */
     int cap, cap3;
@@ -92,6 +96,8 @@ struct RaShared {
     unsigned* bcount;         /* [R]   records in each move bucket                          */
     unsigned* m3count;        /* [RA_M3RING]                                                */
     unsigned *N, *l1, *l1pos, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each      */
+    unsigned* hist;           /* [RA_HBINS] singleton scans per index bin (grant selection) */
+    unsigned* sIdx;           /* [RA_SCAP]  first singleton indices of the ms                */
     int grantCheck, activeCheck, acOld, nArr, overflow, pad0;
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant;
@@ -121,9 +127,19 @@ RA_HD unsigned ra_rec_ts(const uint4& r)   { return r.z & 0xFFFFu; }
 RA_HD unsigned ra_rec_fail(const uint4& r) { return r.z >> 16; }
 RA_HD unsigned ra_z(unsigned ts, unsigned fail) { return (ts & 0xFFFFu) | (fail << 16); }
 
+/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1 (0 for d==1).
+ * floor(x*magic/2^32) is q or q+1 (error < x/2^32 < 1/2), so one conditional add fixes it. */
+RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
+RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic) {
+    if (magic == 0) return 0;
+    unsigned q = rach_mulhi32(x, magic);
+    int r = (int)(x - q * d);
+    return (unsigned)(r < 0 ? r + (int)d : r);
+}
+
 /* slot alignment, W:518-527 (= W:544-553, W:688-697) */
-RA_HD int ra_align(int subTime, int A) {
-    int r = subTime % A;
+RA_HD int ra_align(int subTime, int A, unsigned magicA) {
+    int r = (int)ra_mod((unsigned)subTime, (unsigned)A, magicA);
     if (r == 0) return subTime + 1;
     if (r == 1) return subTime;
     return subTime + (A - r + 1);
@@ -141,7 +157,18 @@ RA_HD unsigned ra_first_scan(const RaShared& s, unsigned p) {     /* s[p] of the
 /* append a record to move bucket `m`; returns its position */
 RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
     unsigned slot = (unsigned)m & (unsigned)(pt.R - 1);
+#ifdef __CUDA_ARCH__
+    /* one shared-memory atomic per distinct bucket per warp instead of one per lane */
+    const unsigned peers = __match_any_sync(__activemask(), slot);
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if ((int)lane == leader) base = atomicAdd(&s.bcount[slot], (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    unsigned pos = base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+#else
     unsigned pos = RA_AADD(&s.bcount[slot], 1u);
+#endif
     if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
     w.bucket[(size_t)slot * w.cap + pos] = rec;
     return pos;
@@ -205,6 +232,7 @@ RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
     for (int i = tid; i < pt.R * pt.P; i += nt) { s.cnt[i] = 0; s.minIP[i] = RA_INF64; }
     for (int i = tid; i < pt.R; i += nt) s.bcount[i] = 0;
     for (int i = tid; i < RA_M3RING; i += nt) s.m3count[i] = 0;
+    for (int i = tid; i < RA_HBINS; i += nt) s.hist[i] = 0;
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
     if (tid == 0) {
         s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0;
@@ -250,12 +278,10 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
  *   [.., +nM3)           Msg3 due: requestResourceAllocation, W:667-710
  * ========================================================================================= */
 template <bool DUMP>
-RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
+RA_HD void ra_phase1_mover(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec) {
     const RaPointDev& pt = *job.pt;
-    const unsigned Rm = (unsigned)(pt.R - 1);
-    if (item < s.nMov) {
+    {
         /* ---------------- mover ---------------- */
-        uint4 rec = w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item];
         if (rec.x == RA_DEAD) return;
         const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
         unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
@@ -264,8 +290,8 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         rach_u32x4 d = ra_draws(job, idx, T);
         if ((int)mrc < pt.M) {
             /* retry branch, W:532-558: outcome does not depend on being postponed */
-            int tmp = (int)(d.v[0] >> 1) % pt.BI;
-            int X = ra_align(T + tmp, pt.A);
+            int tmp = (int)ra_mod(d.v[0] >> 1, (unsigned)pt.BI, pt.magicBI);
+            int X = ra_align(T + tmp, pt.A, pt.magicA);
             mrc++; ptc++;
             if (ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
             uint4 nr = make_uint4(idx, (unsigned)X, rec.z, ra_w3(p0, mrc, ptc, 0));
@@ -283,21 +309,21 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         } else {
             /* limit branch, W:498-531: subTime = CURRENT txTime + tmp (W:516) */
             acc.contFailed++;
-            unsigned pnew = (d.v[0] >> 1) % (unsigned)pt.P;
-            int tmp = (int)(d.v[1] >> 1) % pt.BI;
+            unsigned pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
+            int tmp = (int)ra_mod(d.v[1] >> 1, (unsigned)pt.BI, pt.magicBI);
             unsigned fail = ra_rec_fail(rec) + 1;
             if (fail > 0xFFFFu) s.overflow = 2;
             if (uncertain) {                                /* txTime is T or T+1: decided in phase 3 */
                 unsigned u = RA_AADD(&s.nUnc, 1u);
                 w.uncertain[u] = make_uint4(item, idx, p0 | 0x80000000u, 0);
-                if (ra_align(T + tmp, pt.A) == T) {
+                if (ra_align(T + tmp, pt.A, pt.magicA) == T) {
                     unsigned c = RA_AADD(&s.nC3, 1u);
                     w.c3[c] = make_uint4(idx, p0, pnew, 0);
                 }
                 return;
             }
             int base = stale ? (int)rec.y : T + 1;          /* visible and above the leader: postponed */
-            int X = ra_align(base + tmp, pt.A);
+            int X = ra_align(base + tmp, pt.A, pt.magicA);
             uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, 1, 0));
             if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;       /* firstTxTime, W:510 */
             if (X == T) {                                   /* only from an old txTime */
@@ -311,12 +337,22 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         }
         return;
     }
+}
+
+template <bool DUMP>
+RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
+    const RaPointDev& pt = *job.pt;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    if (item < s.nMov) {
+        ra_phase1_mover<DUMP>(job, w, s, acc, T, item, w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item]);
+        return;
+    }
     item -= s.nMov;
     if (item < (unsigned)s.nArr) {
         /* ---------------- arrival, W:383-394 + first draw W:477-487 ---------------- */
         unsigned idx = (unsigned)s.acOld + item;
         rach_u32x4 d = ra_draws(job, idx, T);
-        unsigned p = (d.v[pt.geometry ? 2 : 0] >> 1) % (unsigned)pt.P;
+        unsigned p = ra_mod(d.v[pt.geometry ? 2 : 0] >> 1, (unsigned)pt.P, pt.magicP);
         uint4 nr = make_uint4(idx, (unsigned)(T + 1), ra_z((unsigned)T, 0), ra_w3(p, 0, 1, 0));
         if (DUMP) {
             int* row = job.dump + (size_t)idx * RA_DUMP_W;
@@ -352,9 +388,9 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         } else {
             /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
             acc.contFailed++;
-            int tmp = (int)(d.v[0] >> 1) % pt.BI;
-            int X = ra_align(T + tmp, 5);
-            unsigned pnew = (d.v[1] >> 1) % (unsigned)pt.P;
+            int tmp = (int)ra_mod(d.v[0] >> 1, (unsigned)pt.BI, pt.magicBI);
+            int X = ra_align(T + tmp, 5, RA_MAGIC5);
+            unsigned pnew = ra_mod(d.v[1] >> 1, (unsigned)pt.P, pt.magicP);
             unsigned fail = ra_rec_fail(rec) + 1;
             if (fail > 0xFFFFu) s.overflow = 2;
             uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, ra_rec_ptc(rec), 0));
@@ -401,10 +437,10 @@ RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     /* limit branch, W:498-531 */
     uint4 rec = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + e.x];
     rach_u32x4 d = ra_draws(job, idx, T);
-    unsigned pnew = (d.v[0] >> 1) % (unsigned)pt.P;
-    int tmp = (int)(d.v[1] >> 1) % pt.BI;
+    unsigned pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
+    int tmp = (int)ra_mod(d.v[1] >> 1, (unsigned)pt.BI, pt.magicBI);
     int base = T + (idx > sp ? 1 : 0);                      /* postponed by the first scan, W:658 */
-    int X = ra_align(base + tmp, pt.A);
+    int X = ra_align(base + tmp, pt.A, pt.magicA);
     uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, ra_rec_fail(rec) + 1), ra_w3(pnew, 0, 1, 0));
     if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;
     if (X == T) ra_lander_push(w, s, nr, pnew == p0 ? 1u : 0u);   /* s.l2 already holds it (phase 2) */
@@ -436,6 +472,13 @@ RA_HD void ra_phase3b_item(const RaWork& w, RaShared& s, unsigned e) {
  *   class items  [0, P):        first scan by the natural leader (a visible non-mover)
  *   lander items [P, P+nLanders): scan by a UE that re-transmits in this ms
  * ========================================================================================= */
+RA_HD void ra_single_push(const RaPointDev& pt, const RaWork& w, RaShared& s, unsigned idx) {
+    unsigned k = RA_AADD(&s.nSingles, 1u);
+    if (k < RA_SCAP) s.sIdx[k] = idx;
+    w.singles[k] = idx;
+    RA_AADD(&s.hist[idx >> pt.hshift], 1u);
+}
+
 RA_HD void ra_count_scan(RaAcc& acc, unsigned size) {
     acc.totScans++;                                         /* B:334,351 */
     if (size == 1) { acc.txop++; }                          /* W:625 */
@@ -451,8 +494,7 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
         s.clsSize[q] = size;
         ra_count_scan(acc, size);
         if (size == 1) {
-            unsigned k = RA_AADD(&s.nSingles, 1u);
-            w.singles[k] = ((ra_u64)sq << 32) | (0x80000000u | q);
+            ra_single_push(pt, w, s, sq);
         }
         return;
     }
@@ -465,8 +507,7 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
     else size = 1u + (meta >> 8);
     ra_count_scan(acc, size);
     if (size == 1) {
-        unsigned k = RA_AADD(&s.nSingles, 1u);
-        w.singles[k] = ((ra_u64)r.x << 32) | l;
+        ra_single_push(pt, w, s, r.x);
     } else {
         w.landerMeta[l] = meta | 2u;                        /* collided */
     }
@@ -484,19 +525,65 @@ RA_HD void ra_phase5_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) 
     if ((long long)n <= K) { s.tau = RA_INF32; }
     else if (K == 0) { s.tau = 0; s.noGrant = 1; }
     else {
-        ra_u64 prev = 0; bool first = true;
+        unsigned prev = 0; bool first = true;
         for (long long r = 0; r < K; ++r) {
-            ra_u64 best = RA_INF64;
+            unsigned best = RA_INF32;
             for (unsigned j = 0; j < n; ++j) {
-                ra_u64 v = w.singles[j];
+                unsigned v = w.singles[j];
                 if ((first || v > prev) && v < best) best = v;
             }
             prev = best; first = false;
         }
-        s.tau = (unsigned)(prev >> 32);
+        s.tau = prev;
     }
     s.grantCheck += (int)n;
 }
+
+#ifdef __CUDACC__
+/* the same threshold computed by one warp: histogram over index bins (filled by phase 4) ->
+ * the bin holding the K-th smallest -> exact rank inside that bin */
+__device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWork& w, RaShared& s, int lane) {
+    const unsigned n = s.nSingles;
+    long long K = (long long)pt.G - 1 - s.grantCheck;
+    if (K < 0) K = 0;
+    unsigned tau = RA_INF32, noGrant = 0;
+    if ((long long)n > K) {
+        if (K == 0) { noGrant = 1; tau = 0; }
+        else {
+            const unsigned k = (unsigned)K;
+            const int per = RA_HBINS / 32;
+            unsigned sum = 0;
+            for (int b = 0; b < per; ++b) sum += s.hist[lane * per + b];
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+            const int L = __ffs(__ballot_sync(0xFFFFFFFFu, incl >= k)) - 1;
+            unsigned bstar = 0, before = 0;
+            if (lane == L) {
+                unsigned c = incl - sum;
+                for (int b = 0; b < per; ++b) {
+                    unsigned h = s.hist[lane * per + b];
+                    if (c + h >= k) { bstar = (unsigned)(lane * per + b); before = c; break; }
+                    c += h;
+                }
+            }
+            bstar = __shfl_sync(0xFFFFFFFFu, bstar, L); before = __shfl_sync(0xFFFFFFFFu, before, L);
+            const unsigned kk = k - before;                 /* 1-based rank inside bin bstar */
+            unsigned prev = 0; bool first = true;
+            for (unsigned r = 0; r < kk; ++r) {
+                unsigned best = RA_INF32;
+                for (unsigned j = lane; j < n; j += 32) {
+                    unsigned v = j < RA_SCAP ? s.sIdx[j] : w.singles[j];
+                    if ((v >> pt.hshift) == bstar && (first || v > prev) && v < best) best = v;
+                }
+                for (int o = 16; o; o >>= 1) { unsigned v = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = v < best ? v : best; }
+                prev = best; first = false;
+            }
+            tau = prev;
+        }
+    }
+    if (lane == 0) { s.tau = tau; s.noGrant = noGrant; s.grantCheck += (int)n; }
+}
+#endif
 
 RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && idx <= s.tau; }
 
@@ -549,6 +636,13 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
         if (w.e1Meta[item]) { r.y = (unsigned)(T + 1); ra_schedule(pt, w, s, r); }
         else ra_park_stale(pt, w, s, T, r);
     }
+}
+
+/* with phase 6 (every thread), only if the ms had singleton scans */
+RA_HD void ra_hist_clear(const RaPointDev& pt, const RaWork& w, RaShared& s, int tid, int nt) {
+    const unsigned n = s.nSingles;
+    if (n > RA_HBINS / 2) { for (int i = tid; i < RA_HBINS; i += nt) s.hist[i] = 0; }
+    else for (unsigned j = tid; j < n; j += nt) s.hist[(j < RA_SCAP ? s.sIdx[j] : w.singles[j]) >> pt.hshift] = 0;
 }
 
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */

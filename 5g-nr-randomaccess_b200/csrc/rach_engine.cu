@@ -26,6 +26,8 @@
 #include "rach_host.h"
 
 #define RA_NT 256          /* threads per block */
+#define RA_NPHASE 10
+#define RA_TICK(k) do { if (tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
 struct RaKernelArgs {
     const RaPointDev* points;
@@ -36,6 +38,7 @@ struct RaKernelArgs {
     ra_stats*         stats;        /* [nJobs]                                   */
     int*              dump;         /* [nJobs][dumpStride] or NULL               */
     int*              errFlag;
+    ra_u64*           phaseCycles;  /* [RA_NPHASE] cycles of thread 0 per phase, summed over blocks */
     size_t            dumpStride;
     int               nJobs, maxP, maxR;
 };
@@ -48,11 +51,12 @@ __device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R
     unsigned* c = reinterpret_cast<unsigned*>(base);
     s.N = c; s.l1 = c + P; s.l1pos = c + 2 * P; s.l1m = c + 3 * P; s.l2 = c + 4 * P;
     s.before = c + 5 * P; s.extraFirst = c + 6 * P; s.clsSize = c + 7 * P;
+    s.hist = c + 8 * P; s.sIdx = s.hist + RA_HBINS;
 }
 
 static size_t ra_smem_bytes(int R, int P) {
     return sizeof(ra_u64) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
-           sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P;
+           sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P + sizeof(unsigned) * (RA_HBINS + RA_SCAP);
 }
 
 template <bool DUMP>
@@ -61,6 +65,9 @@ __global__ void __launch_bounds__(RA_NT) ra_step_kernel(RaKernelArgs a) {
     __shared__ RaShared s;
     __shared__ RaPointDev sPt;
     __shared__ int sJob;
+    __shared__ ra_u64 sCyc[RA_NPHASE];
+    long long tick = 0;
+    if (threadIdx.x < RA_NPHASE) sCyc[threadIdx.x] = 0;
     const int tid = threadIdx.x, nt = blockDim.x;
     const RaWork w = a.works[blockIdx.x];
 
@@ -83,42 +90,65 @@ __global__ void __launch_bounds__(RA_NT) ra_step_kernel(RaKernelArgs a) {
         __syncthreads();
 
         int simTime = pt.maxTime;
+        if (tid == 0) tick = clock64();
         for (int T = 0;; ++T) {
             ra_phase0(job, s, T, tid, nt);
             __syncthreads();
+            RA_TICK(0);
             {
-                const unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-                for (unsigned i = tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
+                /* movers: 128-bit coalesced loads of bucket T, next record in flight while this one is processed */
+                const unsigned nMov = s.nMov;
+                const uint4* bT = w.bucket + (size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap;
+                unsigned i = tid;
+                uint4 cur = make_uint4(RA_DEAD, 0, 0, 0);
+                if (i < nMov) cur = bT[i];
+                while (i < nMov) {
+                    const unsigned ni = i + nt;
+                    uint4 nxt = make_uint4(RA_DEAD, 0, 0, 0);
+                    if (ni < nMov) nxt = bT[ni];
+                    ra_phase1_mover<DUMP>(job, w, s, acc, T, i, cur);
+                    cur = nxt; i = ni;
+                }
+                const unsigned n1 = nMov + (unsigned)s.nArr + s.nM3;
+                for (i = nMov + tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
             }
             __syncthreads();
+            RA_TICK(1);
             if (s.nC3) {
                 if (tid == 0) ra_phase2_serial(w, s);
                 __syncthreads();
+                RA_TICK(2);
             }
             if (s.nUnc) {
                 const unsigned n = s.nUnc;
                 for (unsigned i = tid; i < n; i += nt) ra_phase3_item<DUMP>(job, w, s, T, i);
                 __syncthreads();
+                RA_TICK(3);
             }
             if (s.nE1) {
                 const unsigned n = s.nE1;
                 for (unsigned i = tid; i < n; i += nt) ra_phase3b_item(w, s, i);
                 __syncthreads();
+                RA_TICK(4);
             }
             {
                 const unsigned n4 = (unsigned)pt.P + s.nLanders;
                 for (unsigned i = tid; i < n4; i += nt) ra_phase4_item(pt, w, s, acc, i);
             }
             __syncthreads();
+            RA_TICK(5);
             if (s.nSingles) {
-                if (tid == 0) ra_phase5_serial(pt, w, s);
+                if (tid < 32) ra_phase5_warp(pt, w, s, tid);
                 __syncthreads();
+                RA_TICK(6);
             }
             {
                 const unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
                 for (unsigned i = tid; i < n6; i += nt) ra_phase6_item<DUMP>(job, w, s, T, i);
+                if (s.nSingles) ra_hist_clear(pt, w, s, tid, nt);
             }
             __syncthreads();
+            RA_TICK(7);
             if (ra_ms_done(pt, s, T, &simTime)) break;
         }
         const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
@@ -142,6 +172,8 @@ __global__ void __launch_bounds__(RA_NT) ra_step_kernel(RaKernelArgs a) {
             if (s.overflow) atomicExch(a.errFlag, s.overflow);
         }
     }
+    __syncthreads();
+    if (tid < RA_NPHASE && sCyc[tid]) atomicAdd(&a.phaseCycles[tid], sCyc[tid]);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -181,7 +213,7 @@ struct RaDev {
     std::vector<int*> dArrCum;
     int* dJobPoint = nullptr; unsigned* dJobRep = nullptr; unsigned* dCounter = nullptr;
     ra_stats* dStats = nullptr; RaWork* dWorks = nullptr; unsigned char* dWorkspace = nullptr;
-    int* dDump = nullptr; int* dErr = nullptr; float* dGeom = nullptr;
+    int* dDump = nullptr; int* dErr = nullptr; float* dGeom = nullptr; ra_u64* dCyc = nullptr;
     int grid = 0; size_t smem = 0;
     cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<ra_stats> hStats;
@@ -214,7 +246,7 @@ static void ra_free_dev(RaDev& d) {
     for (int* p : d.dArrCum) cudaFree(p);
     cudaFree(d.dPoints); cudaFree(d.dJobPoint); cudaFree(d.dJobRep); cudaFree(d.dCounter);
     cudaFree(d.dStats); cudaFree(d.dWorks); cudaFree(d.dWorkspace); cudaFree(d.dDump); cudaFree(d.dErr);
-    cudaFree(d.dGeom);
+    cudaFree(d.dGeom); cudaFree(d.dCyc);
     if (d.e0) cudaEventDestroy(d.e0);
     if (d.e1) cudaEventDestroy(d.e1);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -254,6 +286,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     RA_CUDA(sim, cudaMemcpy(d.dJobRep, jr.data(), sizeof(unsigned) * nJobs, cudaMemcpyHostToDevice));
     RA_CUDA(sim, cudaMalloc(&d.dCounter, sizeof(unsigned)));
     RA_CUDA(sim, cudaMalloc(&d.dErr, sizeof(int)));
+    RA_CUDA(sim, cudaMalloc(&d.dCyc, sizeof(ra_u64) * RA_NPHASE));
     RA_CUDA(sim, cudaMalloc(&d.dStats, sizeof(ra_stats) * std::max(nJobs, 1)));
     d.hStats.resize(nJobs);
     if (sim->opt.dumpUEs) {
@@ -283,7 +316,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     const size_t oLMeta = off;     off = ra_align_up(off + sizeof(unsigned) * cap, 256);
     const size_t oUnc = off;       off = ra_align_up(off + sizeof(uint4) * cap, 256);
     const size_t oC3 = off;        off = ra_align_up(off + sizeof(uint4) * cap, 256);
-    const size_t oSingles = off;   off = ra_align_up(off + sizeof(ra_u64) * cap, 256);
+    const size_t oSingles = off;   off = ra_align_up(off + sizeof(unsigned) * cap, 256);
     const size_t oE1 = off;        off = ra_align_up(off + sizeof(uint4) * cap3, 256);
     const size_t oE1Meta = off;    off = ra_align_up(off + sizeof(unsigned) * cap3, 256);
     const size_t perBlock = off;
@@ -306,7 +339,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
         w.bucket = (uint4*)(base + oBucket); w.msg3 = (uint4*)(base + oMsg3);
         w.landerRec = (uint4*)(base + oLander); w.landerMeta = (unsigned*)(base + oLMeta);
         w.uncertain = (uint4*)(base + oUnc); w.c3 = (uint4*)(base + oC3);
-        w.singles = (ra_u64*)(base + oSingles); w.e1Rec = (uint4*)(base + oE1);
+        w.singles = (unsigned*)(base + oSingles); w.e1Rec = (uint4*)(base + oE1);
         w.e1Meta = (unsigned*)(base + oE1Meta); w.cap = sim->cap; w.cap3 = sim->cap3;
     }
     RA_CUDA(sim, cudaMalloc(&d.dWorks, sizeof(RaWork) * grid));
@@ -340,6 +373,7 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
         pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry ? 1 : 0; pt.R = ra_host_ring(&p);
         pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.arrCum = nullptr;
+        ra_host_fill_point(&pt);
         sim->hostPoints.push_back(pt);
         sim->arrCum.emplace_back(pt.nOcc);
         ra_host_arrcum(&p, sim->arrCum.back().data(), pt.nOcc);
@@ -391,9 +425,10 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         RA_CUDA(sim, cudaSetDevice(d.id));
         RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
         RA_CUDA(sim, cudaMemsetAsync(d.dErr, 0, sizeof(int), d.stream));
+        RA_CUDA(sim, cudaMemsetAsync(d.dCyc, 0, sizeof(ra_u64) * RA_NPHASE, d.stream));
         RaKernelArgs a;
         a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
-        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr;
+        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = d.dCyc;
         a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
         RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
         if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
@@ -468,6 +503,21 @@ extern "C" int ra_sim_geometry(ra_sim* sim, int point, int rep, float* out) {
     RA_CUDA(sim, cudaGetLastError());
     RA_CUDA(sim, cudaMemcpyAsync(out, d.dGeom, sizeof(float) * 6 * (size_t)n, cudaMemcpyDeviceToHost, d.stream));
     RA_CUDA(sim, cudaStreamSynchronize(d.stream));
+    return RA_OK;
+}
+
+/* debug/profiling: cycles thread 0 of every block spent up to the barrier that ends each phase
+ * (0 setup, 1 events, 2 C3 resolve, 3 uncertain, 4 late restarts, 5 scans, 6 grants, 7 apply) */
+extern "C" int ra_sim_phase_cycles(ra_sim* sim, unsigned long long* out10) {
+    if (!sim || !out10) return RA_E_INVAL;
+    for (int k = 0; k < RA_NPHASE; ++k) out10[k] = 0;
+    for (RaDev& d : sim->devs) {
+        if (d.jobs.empty()) continue;
+        ra_u64 h[RA_NPHASE];
+        RA_CUDA(sim, cudaSetDevice(d.id));
+        RA_CUDA(sim, cudaMemcpy(h, d.dCyc, sizeof h, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < RA_NPHASE; ++k) out10[k] += h[k];
+    }
     return RA_OK;
 }
 

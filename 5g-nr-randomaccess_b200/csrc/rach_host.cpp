@@ -12,6 +12,7 @@
 
 #include "rach_gpu.h"
 #include "rach_host.h"
+#include "rach_core.cuh"
 
 #define betaF 0.0165
 
@@ -116,6 +117,15 @@ int ra_host_arrcum(const ra_params* p, int* arrCum, int nOcc) {
     }
     delete[] arr;
     return ac;
+}
+
+void ra_host_fill_point(RaPointDev* pt) {
+    pt->magicBI = ra_magic((unsigned)pt->BI);
+    pt->magicP = ra_magic((unsigned)pt->P);
+    pt->magicA = ra_magic((unsigned)pt->A);
+    int sh = 0;
+    while (((pt->nUE - 1) >> sh) >= RA_HBINS) ++sh;
+    pt->hshift = sh;
 }
 
 extern "C" const char* ra_version(void) { return "rach_b200 0.1 (sm_100a, variant W/B)"; }

@@ -8,4 +8,7 @@ int ra_host_validate(const ra_params* p, char* err, size_t errLen);
 int ra_host_ring(const ra_params* p);                          /* R: power of two > BI + max(A,5) + Wn */
 int ra_host_arrcum(const ra_params* p, int* arrCum, int nOcc); /* returns the final activeCheck */
 
+struct RaPointDev;
+void ra_host_fill_point(RaPointDev* pt);                        /* derived fields: magic numbers, hshift */
+
 #endif

@@ -119,6 +119,8 @@ int         ra_sim_dump_ues(ra_sim* sim, int point, int rep, int* out);
 int         ra_sim_geometry(ra_sim* sim, int point, int rep, float* out);
 double      ra_sim_kernel_ms(const ra_sim* sim);     /* device time of the last run (max over devices) */
 long long   ra_sim_gpu_launches(const ra_sim* sim);  /* kernels launched by the last run */
+/* profiling aid: cycles spent per engine phase by thread 0 of every block, summed (out[10]) */
+int         ra_sim_phase_cycles(ra_sim* sim, unsigned long long* out10);
 void        ra_sim_destroy(ra_sim* sim);
 const char* ra_sim_last_error(const ra_sim* sim);
 

@@ -36,6 +36,7 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
     pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry; pt.R = ra_host_ring(&p);
     pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed;
+    ra_host_fill_point(&pt);
     std::vector<int> arrCum(pt.nOcc);
     ra_host_arrcum(&p, arrCum.data(), pt.nOcc);
     pt.arrCum = arrCum.data();
@@ -45,16 +46,17 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     std::vector<uint4> bucket((size_t)pt.R * w.cap), msg3((size_t)RA_M3RING * w.cap3), landerRec(w.cap),
         uncertain(w.cap), c3(w.cap), e1Rec(w.cap3);
     std::vector<unsigned> landerMeta(w.cap), e1Meta(w.cap3);
-    std::vector<ra_u64> singles(w.cap);
+    std::vector<unsigned> singles(w.cap);
     w.bucket = bucket.data(); w.msg3 = msg3.data(); w.landerRec = landerRec.data();
     w.landerMeta = landerMeta.data(); w.uncertain = uncertain.data(); w.c3 = c3.data();
     w.singles = singles.data(); w.e1Rec = e1Rec.data(); w.e1Meta = e1Meta.data();
 
     RaShared s; memset(&s, 0, sizeof s);
-    std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8);
+    std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8), hist(RA_HBINS), sIdx(RA_SCAP);
     std::vector<ra_u64> minIP((size_t)pt.R * pt.P);
     s.cnt = cnt.data(); s.minIP = minIP.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
     s.N = cls.data(); s.l1 = s.N + pt.P; s.l1pos = s.l1 + pt.P; s.l1m = s.l1pos + pt.P; s.l2 = s.l1m + pt.P;
+    s.hist = hist.data(); s.sIdx = sIdx.data();
     s.before = s.l2 + pt.P; s.extraFirst = s.before + pt.P; s.clsSize = s.extraFirst + pt.P;
 
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
@@ -74,6 +76,7 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
         if (s.nSingles) ra_phase5_serial(pt, w, s);
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
+        if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
         if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
         if (ra_ms_done(pt, s, T, &simTime)) break;
     }
