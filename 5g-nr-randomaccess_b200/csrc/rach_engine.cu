@@ -26,6 +26,7 @@
 #include "rach_host.h"
 
 #define RA_NT 256          /* threads per block */
+#define RA_MINB 4            /* resident blocks per SM the register budget is sized for */
 #define RA_NPHASE 10
 #define RA_TICK(k) do { if (tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
@@ -60,7 +61,7 @@ static size_t ra_smem_bytes(int R, int P) {
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(RA_NT) ra_step_kernel(RaKernelArgs a) {
+__global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a) {
     extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
     __shared__ RaShared s;
     __shared__ RaPointDev sPt;
