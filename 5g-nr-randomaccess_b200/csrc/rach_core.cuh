@@ -92,15 +92,15 @@ struct RaWork {
 /* ---- per-CTA shared state ---------------------------------------------------------------- */
 struct RaShared {
     unsigned* cnt;            /* [R*P] cohort size                                          */
-    ra_u64*   minIP;          /* [R*P] lowest (idx<<32 | pos in bucket) of the cohort        */
+    unsigned* minI;           /* [R*P] lowest UE index of the cohort                         */
     unsigned* bcount;         /* [R]   records in each move bucket                          */
     unsigned* m3count;        /* [RA_M3RING]                                                */
-    unsigned *N, *l1, *l1pos, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each      */
+    unsigned *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each     */
     unsigned* hist;           /* [RA_HBINS] singleton scans per index bin (grant selection) */
     unsigned* sIdx;           /* [RA_SCAP]  first singleton indices of the ms                */
     int grantCheck, activeCheck, acOld, nArr, overflow, pad0;
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
-    unsigned nSuccess, noGrant;
+    unsigned nSuccess, noGrant, nNl, pad1;
     ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
 };
 
@@ -127,14 +127,16 @@ RA_HD unsigned ra_rec_ts(const uint4& r)   { return r.z & 0xFFFFu; }
 RA_HD unsigned ra_rec_fail(const uint4& r) { return r.z >> 16; }
 RA_HD unsigned ra_z(unsigned ts, unsigned fail) { return (ts & 0xFFFFu) | (fail << 16); }
 
-/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1 (0 for d==1).
- * floor(x*magic/2^32) is q or q+1 (error < x/2^32 < 1/2), so one conditional add fixes it. */
-RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
+/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1
+ * (0xFFFFFFFF for d==1).  floor(x*magic/2^32) is q or q+1 for d >= 2 (error < x/2^32 < 1/2)
+ * and x-1 for d == 1, so two conditional corrections make the remainder exact. */
+RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ull / d) + 1u; }
 RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic) {
-    if (magic == 0) return 0;
     unsigned q = rach_mulhi32(x, magic);
     int r = (int)(x - q * d);
-    return (unsigned)(r < 0 ? r + (int)d : r);
+    if (r < 0) r += (int)d;
+    if (r >= (int)d) r -= (int)d;
+    return (unsigned)r;
 }
 
 /* slot alignment, W:518-527 (= W:544-553, W:688-697) */
@@ -178,10 +180,10 @@ RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s
  * its RAR window expires at X + Wn - 1 (rarWindow is 1 at X, W:493) */
 RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec) {
     int m = (int)rec.y + pt.Wn - 1;
-    unsigned pos = ra_bucket_push(pt, w, s, m, rec);
+    ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
     RA_AADD(&s.cnt[c], 1u);
-    RA_AMIN(&s.minIP[c], ((ra_u64)rec.x << 32) | pos);
+    RA_AMIN(&s.minI[c], rec.x);
 }
 
 /* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old
@@ -229,7 +231,7 @@ RA_HD int ra_sector(int r31) {
 template <bool DUMP>
 RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
     const RaPointDev& pt = *job.pt;
-    for (int i = tid; i < pt.R * pt.P; i += nt) { s.cnt[i] = 0; s.minIP[i] = RA_INF64; }
+    for (int i = tid; i < pt.R * pt.P; i += nt) { s.cnt[i] = 0; s.minI[i] = RA_INF32; }
     for (int i = tid; i < pt.R; i += nt) s.bcount[i] = 0;
     for (int i = tid; i < RA_M3RING; i += nt) s.m3count[i] = 0;
     for (int i = tid; i < RA_HBINS; i += nt) s.hist[i] = 0;
@@ -250,19 +252,19 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
     const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1);
     for (int p = tid; p < P; p += nt) {
-        unsigned n = 0; ra_u64 best = RA_INF64; unsigned bestm = 0;
+        unsigned n = 0, best = RA_INF32, bestm = 0;
         for (int d = 0; d < Wn; ++d) {
             unsigned m = ((unsigned)(T + d) & Rm);
             n += s.cnt[m * P + p];
-            if (d > 0) { ra_u64 v = s.minIP[m * P + p]; if (v < best) { best = v; bestm = m; } }
+            if (d > 0) { unsigned v = s.minI[m * P + p]; if (v < best) { best = v; bestm = m; } }
         }
         s.N[p] = n;
-        s.l1[p] = (unsigned)(best >> 32); s.l1pos[p] = (unsigned)best; s.l1m[p] = bestm;
+        s.l1[p] = best; s.l1m[p] = bestm;
         s.l2[p] = RA_INF32; s.before[p] = 0; s.extraFirst[p] = 0; s.clsSize[p] = 0;
     }
     if (tid == 0) {
         if (T % 5 == 0) s.grantCheck = 0;                       /* literal 5, W:268 */
-        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0;
+        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
         s.acOld = s.activeCheck;
         if (T % pt.A == 0 && s.activeCheck != pt.nUE) s.activeCheck = pt.arrCum[T / pt.A];
         s.nArr = s.activeCheck - s.acOld;
@@ -280,62 +282,50 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
 template <bool DUMP>
 RA_HD void ra_phase1_mover(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec) {
     const RaPointDev& pt = *job.pt;
-    {
-        /* ---------------- mover ---------------- */
-        if (rec.x == RA_DEAD) return;
-        const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
-        unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
-        /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
-        const bool uncertain = !stale && idx < s.l1[p0];
-        rach_u32x4 d = ra_draws(job, idx, T);
-        if ((int)mrc < pt.M) {
-            /* retry branch, W:532-558: outcome does not depend on being postponed */
-            int tmp = (int)ra_mod(d.v[0] >> 1, (unsigned)pt.BI, pt.magicBI);
-            int X = ra_align(T + tmp, pt.A, pt.magicA);
-            mrc++; ptc++;
-            if (ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
-            uint4 nr = make_uint4(idx, (unsigned)X, rec.z, ra_w3(p0, mrc, ptc, 0));
-            if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 4] = X;          /* secondTxTime, W:557 */
-            if (uncertain) {
-                unsigned u = RA_AADD(&s.nUnc, 1u);
-                w.uncertain[u] = make_uint4(item, idx, p0, 0);
-            }
-            if (X == T) {                                   /* backoff 0 on a tx slot: transmits now */
-                RA_AMIN(&s.l2[p0], idx);
-                ra_lander_push(w, s, nr, stale ? 0u : 1u);
-            } else {
-                ra_schedule(pt, w, s, nr);
-            }
-        } else {
-            /* limit branch, W:498-531: subTime = CURRENT txTime + tmp (W:516) */
-            acc.contFailed++;
-            unsigned pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
-            int tmp = (int)ra_mod(d.v[1] >> 1, (unsigned)pt.BI, pt.magicBI);
-            unsigned fail = ra_rec_fail(rec) + 1;
-            if (fail > 0xFFFFu) s.overflow = 2;
-            if (uncertain) {                                /* txTime is T or T+1: decided in phase 3 */
-                unsigned u = RA_AADD(&s.nUnc, 1u);
-                w.uncertain[u] = make_uint4(item, idx, p0 | 0x80000000u, 0);
-                if (ra_align(T + tmp, pt.A, pt.magicA) == T) {
-                    unsigned c = RA_AADD(&s.nC3, 1u);
-                    w.c3[c] = make_uint4(idx, p0, pnew, 0);
-                }
-                return;
-            }
-            int base = stale ? (int)rec.y : T + 1;          /* visible and above the leader: postponed */
-            int X = ra_align(base + tmp, pt.A, pt.magicA);
-            uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, 1, 0));
-            if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;       /* firstTxTime, W:510 */
-            if (X == T) {                                   /* only from an old txTime */
-                RA_AMIN(&s.l2[pnew], idx);
-                ra_lander_push(w, s, nr, 0u);
-            } else if (X > T) {
-                ra_schedule(pt, w, s, nr);
-            } else {
-                ra_park_stale(pt, w, s, T, nr);
-            }
+    if (rec.x == RA_DEAD) return;
+    const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
+    unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
+    /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
+    const bool uncertain = !stale && idx < s.l1[p0];
+    const rach_u32x4 d = ra_draws(job, idx, T);
+    const bool limit = (int)mrc >= pt.M;
+    /* both branches draw the backoff: retry W:540 (1st draw), limit W:514 (2nd draw) */
+    const int tmp = (int)ra_mod((limit ? d.v[1] : d.v[0]) >> 1, (unsigned)pt.BI, pt.magicBI);
+    unsigned pnew = p0, z = rec.z;
+    int base = T;                                           /* retry: subTime = time + tmp, W:542 */
+    if (limit) {
+        /* limit branch, W:498-531: new preamble, counters reset, subTime = CURRENT txTime + tmp (W:516):
+         * an old txTime if stale, T+1 if a lower index postponed me (certain above the leader),
+         * T under the not-postponed hypothesis if uncertain (settled in phase 3) */
+        acc.contFailed++;
+        pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
+        const unsigned fail = ra_rec_fail(rec) + 1;
+        if (fail > 0xFFFFu) s.overflow = 2;
+        z = ra_z((unsigned)T, fail); mrc = 0; ptc = 1;
+        base = stale ? (int)rec.y : (uncertain ? T : T + 1);
+    } else {
+        /* retry branch, W:532-558 */
+        mrc++; ptc++;
+        if (ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
+    }
+    const int X = ra_align(base + tmp, pt.A, pt.magicA);
+    const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
+    if (uncertain) {
+        unsigned u = RA_AADD(&s.nUnc, 1u);
+        w.uncertain[u] = make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0);
+        if (limit) {
+            if (X == T) { unsigned c = RA_AADD(&s.nC3, 1u); w.c3[c] = make_uint4(idx, p0, pnew, 0); }
+            return;
         }
-        return;
+    }
+    if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + (limit ? 3 : 4)] = limit ? T + 1 : X;   /* W:510 / W:557 */
+    if (X > T) {
+        ra_schedule(pt, w, s, nr);                          /* the common case, one call site */
+    } else if (X == T) {                                    /* backoff 0 on a tx slot: transmits now */
+        RA_AMIN(&s.l2[pnew], idx);
+        ra_lander_push(w, s, nr, (!stale && !limit) ? 1u : 0u);
+    } else {
+        ra_park_stale(pt, w, s, T, nr);                     /* only from an old txTime */
     }
 }
 
@@ -599,21 +589,12 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
         const unsigned q = item;
         const unsigned sq = ra_first_scan(s, q);
         if (sq != RA_INF32 && sq == s.l1[q] && s.clsSize[q] == 1 && ra_granted(s, sq)) {
-            /* the natural leader is alone and granted: active=2, txTime=T+11, W:642-645 */
-            const size_t at = (size_t)s.l1m[q] * w.cap + s.l1pos[q];
-            uint4 rec = w.bucket[at];
-            w.bucket[at].x = RA_DEAD;
-            s.cnt[s.l1m[q] * pt.P + q] -= 1; s.minIP[s.l1m[q] * pt.P + q] = RA_INF64;
-            if (DUMP) {
-                int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
-                row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
-            }
-            rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
-            ra_msg3_push(w, s, T + 11, rec);
+            unsigned k = RA_AADD(&s.nNl, 1u);               /* handled by ra_phase6b (needs the record) */
+            s.nlList[k] = q;
         }
         if (q == 0) { s.bcount[(unsigned)T & Rm] = 0; s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
         /* the cohort that moved in this ms is gone */
-        s.cnt[((unsigned)T & Rm) * pt.P + q] = 0; s.minIP[((unsigned)T & Rm) * pt.P + q] = RA_INF64;
+        s.cnt[((unsigned)T & Rm) * pt.P + q] = 0; s.minI[((unsigned)T & Rm) * pt.P + q] = RA_INF32;
         return;
     }
     item -= (unsigned)pt.P;
@@ -635,6 +616,31 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
         uint4 r = w.e1Rec[item];
         if (w.e1Meta[item]) { r.y = (unsigned)(T + 1); ra_schedule(pt, w, s, r); }
         else ra_park_stale(pt, w, s, T, r);
+    }
+}
+
+/* Phase 6b (every thread, only if nNl > 0) -- a visible non-mover that scanned alone and was
+ * granted: active=2, txTime=T+11, W:642-645.  Its record sits somewhere in the bucket of its
+ * move time; find it by index, retire it from bucket and cohort, queue Msg3. */
+template <bool DUMP>
+RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
+    const RaPointDev& pt = *job.pt;
+    for (unsigned e = 0; e < s.nNl; ++e) {
+        const unsigned q = s.nlList[e], slot = s.l1m[q], want = s.l1[q];
+        const unsigned n = s.bcount[slot];
+        for (unsigned j = tid; j < n; j += nt) {
+            const size_t at = (size_t)slot * w.cap + j;
+            if (w.bucket[at].x != want) continue;
+            uint4 rec = w.bucket[at];
+            w.bucket[at].x = RA_DEAD;
+            s.cnt[slot * pt.P + q] -= 1; s.minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
+            if (DUMP) {
+                int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
+                row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
+            }
+            rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
+            ra_msg3_push(w, s, T + 11, rec);
+        }
     }
 }
 

@@ -45,18 +45,18 @@ struct RaKernelArgs {
 };
 
 __device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R, int P) {
-    s.minIP = reinterpret_cast<ra_u64*>(base);                 base += sizeof(ra_u64) * (size_t)R * P;
+    s.minI = reinterpret_cast<unsigned*>(base);                base += sizeof(unsigned) * (size_t)R * P;
     s.cnt = reinterpret_cast<unsigned*>(base);                 base += sizeof(unsigned) * (size_t)R * P;
     s.bcount = reinterpret_cast<unsigned*>(base);              base += sizeof(unsigned) * (size_t)R;
     s.m3count = reinterpret_cast<unsigned*>(base);             base += sizeof(unsigned) * RA_M3RING;
     unsigned* c = reinterpret_cast<unsigned*>(base);
-    s.N = c; s.l1 = c + P; s.l1pos = c + 2 * P; s.l1m = c + 3 * P; s.l2 = c + 4 * P;
+    s.N = c; s.l1 = c + P; s.nlList = c + 2 * P; s.l1m = c + 3 * P; s.l2 = c + 4 * P;
     s.before = c + 5 * P; s.extraFirst = c + 6 * P; s.clsSize = c + 7 * P;
     s.hist = c + 8 * P; s.sIdx = s.hist + RA_HBINS;
 }
 
 static size_t ra_smem_bytes(int R, int P) {
-    return sizeof(ra_u64) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
+    return sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
            sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P + sizeof(unsigned) * (RA_HBINS + RA_SCAP);
 }
 
@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
             }
             __syncthreads();
             RA_TICK(7);
+            if (s.nNl) {
+                ra_phase6b<DUMP>(job, w, s, T, tid, nt);
+                __syncthreads();
+                RA_TICK(8);
+            }
             if (ra_ms_done(pt, s, T, &simTime)) break;
         }
         const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;

@@ -53,9 +53,9 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
 
     RaShared s; memset(&s, 0, sizeof s);
     std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8), hist(RA_HBINS), sIdx(RA_SCAP);
-    std::vector<ra_u64> minIP((size_t)pt.R * pt.P);
-    s.cnt = cnt.data(); s.minIP = minIP.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
-    s.N = cls.data(); s.l1 = s.N + pt.P; s.l1pos = s.l1 + pt.P; s.l1m = s.l1pos + pt.P; s.l2 = s.l1m + pt.P;
+    std::vector<unsigned> minI((size_t)pt.R * pt.P);
+    s.cnt = cnt.data(); s.minI = minI.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
+    s.N = cls.data(); s.l1 = s.N + pt.P; s.nlList = s.l1 + pt.P; s.l1m = s.nlList + pt.P; s.l2 = s.l1m + pt.P;
     s.hist = hist.data(); s.sIdx = sIdx.data();
     s.before = s.l2 + pt.P; s.extraFirst = s.before + pt.P; s.clsSize = s.extraFirst + pt.P;
 
@@ -77,6 +77,7 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
         if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
+        if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
         if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
         if (ra_ms_done(pt, s, T, &simTime)) break;
     }
