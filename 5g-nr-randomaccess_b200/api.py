@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librach_gpu.so")
+LIB_PATH = os.environ.get("RACH_GPU_LIB") or os.path.join(HERE, "librach_gpu.so")   # override: tuning builds only
 
 RA_VARIANT_W, RA_VARIANT_U0, RA_VARIANT_N = 0, 1, 2
 RA_DUMP_FIELDS = 16

@@ -25,8 +25,12 @@
 #include "rach_gpu.h"
 #include "rach_host.h"
 
+#ifndef RA_NT
 #define RA_NT 256          /* threads per block */
-#define RA_MINB 4            /* resident blocks per SM the register budget is sized for */
+#endif
+#ifndef RA_MINB
+#define RA_MINB (1024 / RA_NT) /* resident blocks per SM the register budget is sized for */
+#endif
 #define RA_NPHASE 10
 #define RA_TICK(k) do { if (tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
@@ -312,7 +316,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     if (sim->opt.dumpUEs) RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<true>, RA_NT, d.smem));
     else RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<false>, RA_NT, d.smem));
     if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
-    int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, 4);
+    int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, RA_MINB);
 
     const size_t cap = (size_t)sim->cap, cap3 = (size_t)sim->cap3;
     size_t off = 0;
