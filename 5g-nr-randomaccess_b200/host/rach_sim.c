@@ -1,0 +1,212 @@
+/*
+ * rach_sim.c -- host program: the command line and report formats of the reference's only CLI
+ * (RandomAccessWithNOMA.c), with the (seed, nUE) loop body replaced by librach_gpu.
+ *
+ *   flags accepted by the reference parser (W:93-158):  -t -d -p -b -g -rc -mrc -s -c -bs -ut
+ *     (and their long forms); same validation messages, same exit status (255), same help text
+ *     on an unknown flag (W:159-204).  The README spells some of them -r -m -u; those are
+ *     accepted here as aliases (a superset; the reference itself rejects them).
+ *   added:  --nue a,b,c  (points; default the reference sweep 10000..100000 step 10000, W:221)
+ *           --no-logs    (skip the per-UE *_Logs.txt, W:797-825)
+ *           --outdir DIR (default "."), --device N, --seed64 S (tape key, default 0)
+ *
+ * Differences that cannot be hidden: randomness is the Philox draw tape keyed by
+ * (seed64, replication = the reference's randomSeed, UE, ms), not libc rand(); the whole sweep
+ * is ONE library call (all points x seeds in one launch), results are printed afterwards in the
+ * reference's order.
+ */
+#include <errno.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include "rach_gpu.h"
+
+static void die(const char* msg) { printf("%s", msg); exit(-1); }
+
+static void usage_and_exit(void) {
+    static const char* rows[][4] = {
+        {"--times         -t", "Simulation times (int)", "Simulation count must be greater than zero.", "Default 1"},
+        {"--distribution  -d", "Traffic model (1 or 2)", NULL, NULL},
+        {"--preambles     -p", "Number of preambles (int)", "Number of preamble must be greater than zero.", "Default 54"},
+        {"--backoff       -b", "Backoff indicator (int)", "Backoff indicator must be greater than zero.", "Default 20"},
+        {"--grant         -g", "The number of Up Link Grant per RAR (int)", "The number of Up Link Grant per RAR must be greater than zero.", "Default 12"},
+        {"--rarCount      -r", "RAR window size (int)", "The maximum RAR window size must be greater than zero.", "Default 5"},
+        {"--maxRar        -m", "Maximum retransmission (int)", "Maximum retransmissions must be greater than zero.", "Default 10"},
+        {"--subframe      -s", "Subframe units (int)", "The size of the subframe must be at least 5. (float)", "Default 5"},
+        {"--cell          -c", "Cell radius Size", "The radius of the cell is entered in diameter units and must be greater than 400m.", "Default 400.0"},
+        {"--hbs           -b", "Height of BS from ground (float)", "The height of the BS must be between 10m and 20m.", "Default 10.0"},
+        {"--hut           -u", "Height of UE from ground (float)", "The height of the UE must be between 1.5m and 22.5m.", "Default 1.8"},
+    };
+    const char* pad = "                     ";
+    for (size_t i = 0; i < sizeof rows / sizeof rows[0]; ++i) {
+        printf("%s : %s\n", rows[i][0], rows[i][1]);
+        if (i == 1) {           /* W:164-166 */
+            printf("%s1: traffic model 1 (Uniform distribution)\n", pad);
+            printf("%s2: traffic model 2 (Beta distribution)\n\n", pad);
+            continue;
+        }
+        printf("%s%s\n", pad, rows[i][2]);
+        printf("%s%s\n\n", pad, rows[i][3]);
+    }
+    exit(-1);
+}
+
+static int is_flag(const char* a, const char* l, const char* s, const char* alias) {
+    return strcmp(a, l) == 0 || strcmp(a, s) == 0 || (alias && strcmp(a, alias) == 0);
+}
+
+int main(int argc, char* argv[]) {
+    ra_params base;
+    ra_params_default(&base, RA_VARIANT_W);
+    int times = 1, writeLogs = 1, device = 0;
+    const char* outdir = ".";
+    int nueList[64], nNue = 0;
+    unsigned long long seed64 = 0;
+
+    for (int i = 1; i < argc; i += 2) {
+        const char* a = argv[i];
+        if (strcmp(a, "--no-logs") == 0) { writeLogs = 0; i -= 1; continue; }
+        const char* v = (i + 1 < argc) ? argv[i + 1] : "";      /* the reference dereferences argv[i+1] blindly (W:94) */
+        if (is_flag(a, "--times", "-t", NULL)) {
+            if (atoi(v) < 1) die("Simulation count must be greater than zero.");
+            times = atoi(v);
+        } else if (is_flag(a, "--distribution", "-d", NULL)) {
+            if (atoi(v) != 1 && atoi(v) != 0) die("Traffic model just choose 1 or 2");       /* W:100-102 */
+            base.distribution = atoi(v);
+        } else if (is_flag(a, "--preambles", "-p", NULL)) {
+            if (atoi(v) < 1) die("Number of preamble must be greater than zero.");
+            base.nPreamble = atoi(v);
+        } else if (is_flag(a, "--backoff", "-b", NULL)) {
+            if (atoi(v) < 1) die("Backoff indicator must be greater than zero.");
+            base.backoffIndicator = atoi(v);
+        } else if (is_flag(a, "--grant", "-g", NULL)) {
+            if (atoi(v) < 1) die("The number of Up Link Grant per RAR must be greater than zero.");
+            base.nGrantUL = atoi(v);
+        } else if (is_flag(a, "--rarCount", "-rc", "-r")) {
+            if (atoi(v) < 1) die("The maximum RAR window size must be greater than zero.");
+            base.maxRarWindow = atoi(v) + 1;                                                  /* W:128 */
+        } else if (is_flag(a, "--maxRar", "-mrc", "-m")) {
+            if (atoi(v) < 1) die("Maximum retransmissions must be greater than zero.");
+            base.maxMsg2TxCount = atoi(v) - 1;                                                /* W:134 */
+        } else if (is_flag(a, "--subframe", "-s", NULL)) {
+            if (atoi(v) < 5) die("The size of the subframe must be at least 5.");
+            base.accessTime = atoi(v);
+        } else if (is_flag(a, "--cell", "-c", NULL)) {
+            if (atof(v) < 400.0) die("The radius of the cell is entered in diameter units and must be greater than 400m.");
+            base.cellRadius = atof(v);
+        } else if (is_flag(a, "--hbs", "-bs", NULL)) {
+            if (atof(v) < 10.0 || atof(v) > 20.0) die("The height of the BS must be between 10m and 20m.");
+            base.hBS = atof(v);
+        } else if (is_flag(a, "--hut", "-ut", "-u")) {
+            if (atof(v) < 1.5 || atof(v) > 22.5) die("The height of the UE must be between 1.5m and 22.5m.");
+            base.hUT = atof(v);
+        } else if (strcmp(a, "--nue") == 0) {
+            char* dup = strdup(v);
+            for (char* tok = strtok(dup, ","); tok && nNue < 64; tok = strtok(NULL, ",")) nueList[nNue++] = atoi(tok);
+            free(dup);
+        } else if (strcmp(a, "--outdir") == 0) { outdir = v;
+        } else if (strcmp(a, "--device") == 0) { device = atoi(v);
+        } else if (strcmp(a, "--seed64") == 0) { seed64 = strtoull(v, NULL, 0);
+        } else usage_and_exit();
+    }
+    if (nNue == 0) for (int n = 10000; n <= 100000; n += 10000) nueList[nNue++] = n;   /* W:221 */
+    base.seed = seed64;
+
+    const int uniform = base.distribution == 1;
+    printf(uniform ? "Traffic model: Uniform\n\n" : "Traffic model: Beta\n\n");          /* W:208-213 */
+
+    char dir[600];
+    snprintf(dir, sizeof dir, "%s/%s", outdir, uniform ? "NomaUniformResults" : "NomaBetaResults");
+    mkdir(outdir, 0755);
+    mkdir(dir, 0755);                                                                    /* W:67-68 */
+
+    ra_params* pts = (ra_params*)calloc((size_t)nNue, sizeof *pts);
+    for (int k = 0; k < nNue; ++k) { pts[k] = base; pts[k].nUE = nueList[k]; }
+    ra_options opt; memset(&opt, 0, sizeof opt);
+    opt.dumpUEs = writeLogs;
+    ra_sim* sim = ra_sim_create_ex(pts, nNue, times, &device, 1, &opt);
+    if (!sim) { fprintf(stderr, "rach_sim: %s\n", ra_last_create_error()); return 2; }
+    if (ra_sim_run(sim) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+
+    for (int seed = 0; seed < times; ++seed) {                   /* W:216 */
+        for (int k = 0; k < nNue; ++k) {                         /* W:221 */
+            const ra_params* p = &pts[k];
+            const int nUE = p->nUE, nPreamble = p->nPreamble;
+            ra_stats st;
+            if (ra_sim_stats(sim, k, seed, &st) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+            const int horizon = ra_horizon_ms(p);
+            int* arr = (int*)malloc(sizeof(int) * (size_t)horizon);
+            ra_arrival_schedule(p, arr, horizon);
+            const int lastMs = st.simTimeMs < horizon ? st.simTimeMs : horizon - 1;
+            int activeCheck = 0;
+            for (int t = 0; t <= lastMs; ++t) activeCheck += arr[t];
+            const int nAccessUE = arr[0];
+            free(arr);
+
+            int* ue = NULL;
+            float totalDelay = 0;                                /* float accumulation in UE order, W:338,346 */
+            if (writeLogs) {
+                ue = (int*)malloc(sizeof(int) * (size_t)nUE * RA_DUMP_FIELDS);
+                if (ra_sim_dump_ues(sim, k, seed, ue) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+                for (int i = 0; i < nUE; ++i) if (ue[i * RA_DUMP_FIELDS + 13] == 1) totalDelay += (float)ue[i * RA_DUMP_FIELDS + 0];
+            } else {
+                totalDelay = (float)st.delaySum;                 /* identical while the sum stays below 2^24 */
+            }
+            const int nSuccessUE = st.nSuccess, failedUEs = nUE - nSuccessUE;
+            const int preambleTxCount = (int)st.preambleTxSum;
+            const int continueFailed = (int)st.continueFailed, finalSuccess = (int)st.finalSuccess;
+            (void)failedUEs;
+
+            printf("-------- %05d Result ---------\n", activeCheck);                     /* W:354 */
+            if (uniform) printf("Number of RA try UEs per Subframe: %d\n", nAccessUE);   /* W:355-357 */
+            printf("Fail Counts: %d\n", (int)st.failCountSum);                           /* W:361 */
+
+            /* W:735-739 */
+            float ratioSuccess = (float)nSuccessUE / (float)nUE * 100.0;
+            float nCollisionPreambles = (float)st.collisionPreambles / ((float)nUE * (float)nPreamble);
+            float averagePreambleTx = (float)preambleTxCount / (float)nSuccessUE;
+            float averageDelay = totalDelay / (float)nSuccessUE;
+            printf("Number of UEs: %d\n", nUE);
+            printf("Total simulation time: %dms\n", st.simTimeMs);
+            printf("Success ratio: %.2lf\n", ratioSuccess);
+            printf("Number of succeed UEs: %d\n", nSuccessUE);
+            printf("Number of falied UEs: %d\n", continueFailed);
+            printf("Number of collision preambles: %.6lf\n", nCollisionPreambles);
+            printf("Average preamble tx count: %.2lf\n", averagePreambleTx);
+            printf("Average delay: %.2lf\n", averageDelay);
+
+            char path[800];
+            snprintf(path, sizeof path, "%s/%d_%d_%d_Results.txt", dir, seed, nPreamble, nUE);   /* W:754-758 */
+            FILE* fp = fopen(path, "w+");
+            if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
+            fprintf(fp, "%d\n%.2lf\n%d\n%.2lf\n%.2lf\n", nUE, ratioSuccess, nSuccessUE, averagePreambleTx, averageDelay);
+            fprintf(fp, "Number of total preamble tx: %d\n", preambleTxCount);
+            fprintf(fp, "Finally Falied: %d\n", continueFailed);
+            fprintf(fp, "Finally Success: %lf\n", (float)finalSuccess / (float)(continueFailed + finalSuccess));
+            fclose(fp);
+
+            if (writeLogs) {                                                             /* W:797-825 */
+                snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.txt", dir, seed, nPreamble, nUE);
+                fp = fopen(path, "w+");
+                if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
+                static const char* names[15] = {"Idx", "Timer", "Active", "txTime", "FirstTxTime", "SecondTxTime", "NowBackoff",
+                    "Preamble", "Preamble change", "RAR window", "Max RAR", "Preamble reTx", "MSG 2 Flag", "ConnectRequest", "MSG 4 Flag"};
+                for (int i = 0; i < nUE; ++i) {
+                    const int* r = ue + (size_t)i * RA_DUMP_FIELDS;
+                    fprintf(fp, "%s: %d", names[0], i);
+                    for (int f = 0; f < 14; ++f) fprintf(fp, " | %s: %d", names[f + 1], r[f]);
+                    fputc('\n', fp);
+                }
+                fclose(fp);
+                free(ue);
+            }
+        }
+    }
+    fprintf(stderr, "rach_sim: %d points x %d seeds, kernel %.1f ms (%s)\n", nNue, times, ra_sim_kernel_ms(sim), ra_version());
+    ra_sim_destroy(sim);
+    free(pts);
+    return 0;
+}

@@ -176,8 +176,7 @@ def run_our_arm(args):
     pkg = importlib.import_module("5g-nr-randomaccess_b200")
     pkg.load_lib()
 
-    reps_local = args.reps if args.scaling == "weak" else (args.reps + world - 1 - rank) // world
-    rep_offset = rank * args.reps if args.scaling == "weak" else sum((args.reps + world - 1 - r) // world for r in range(rank))
+    reps_local, rep_offset = pkg.shard_plan(args.reps, world, rank, args.scaling)
     p = pkg.default_params(nUE=args.nue, seed=args.seed)
     if args.distribution == "uniform":
         p.distribution = 1
@@ -205,16 +204,15 @@ def run_our_arm(args):
     clocks = sampler.stop()
 
     st = sim.stats_all()
-    updates_local = int(st["updates"].sum())
     stats_bytes = st.nbytes
     t = torch.tensor([kernel_ms, wall_ms], dtype=torch.float64, device="cuda")
-    u = torch.tensor([updates_local, int(st["nSuccess"].sum()), int(st["preambleTxSum"].sum()),
-                      int(st["delaySum"].sum()), reps_local], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)            # max over ranks of the device time
-        dist.all_reduce(u, op=dist.ReduceOp.SUM)            # the one small allreduce of counters (NCCL)
+    # the one small all-reduce of the per-replication counters (NCCL over NVLink when world > 1)
+    tot = pkg.allreduce_counters(pkg.local_counter_vector(st), dist if world > 1 else None, device="cuda")
     kernel_ms, wall_ms = float(t[0]), float(t[1])
-    updates, n_succ, tx_sum, delay_sum, reps_total = (int(x) for x in u)
+    updates, n_succ, tx_sum, delay_sum, reps_total = (tot["updates"], tot["nSuccess"], tot["preambleTxSum"],
+                                                      tot["delaySum"], tot["replications"])
 
     if rank == 0:
         peak, peak_src = peaks()

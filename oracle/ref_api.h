@@ -20,7 +20,7 @@ typedef struct ref_config {
     int rep;
     int useTape;            /* 1 = Philox draw tape, 0 = libc rand() seeded with (unsigned)seed */
     int stopMs;             /* >0: abandon the run when a draw is requested at ms >= stopMs    */
-    int echo;               /* 1 = let the reference's printf through                          */
+    int echo;               /* 1 = let the reference's printf through; 2 = also write its result files */
 } ref_config;
 
 typedef struct ref_result {

@@ -125,6 +125,7 @@ int ref_printf_hook(const char* fmt, ...) {
 }
 
 FILE* ref_fopen_hook(const char* name, const char* mode) {
+    if (g_cfg.echo >= 2) return fopen(name, mode);     /* format tests: real files in the cwd */
     (void)name; (void)mode;
     return fopen("/dev/null", "w");
 }
