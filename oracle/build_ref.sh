@@ -50,4 +50,17 @@ SWEEP='s/for (int n = 10000; n <= 100000; n += 10000)/for (int n = ref_nue; n <=
   echo; echo '#define REF_VARIANT 1'; echo '#include "ref_shim_post.h"'
 } | $CC $CFLAGS -x c - -o "$out/libref_b.so" -lm
 
+# ---- N: NOMA.c ---------------------------------------------------------------------------
+#   N:644  seed loop 0..9 -> one seed;  N:648  nUE sweep -> ref_nue
+#   N:499-546 (resourceRequestAllocation: `user` is the array) rand() -> keyed by (user+i)->idx
+#   N:194-324 (preambleSectorCollisionDetection)              rand() -> base-station stream (sector s)
+{ echo '#include "ref_shim_pre.h"'
+  sed -e '644s/seed < 10/seed < 1/' \
+      -e '648s/for (int nUE = 10000; nUE <= 100000; nUE += 10000)/for (int nUE = ref_nue; nUE <= ref_nue; nUE += 10000)/' \
+      -e '499,546s/rand()/ref_tape_rand((user + i)->idx, time)/g' \
+      -e '194,324s/rand()/ref_tape_rand_bs(s, time)/g' \
+      "$ref/NOMA.c"
+  echo; echo '#include "ref_shim_post_n.h"'
+} | $CC $CFLAGS -x c - -o "$out/libref_n.so" -lm
+
 echo "built: $(ls "$out")"

@@ -62,12 +62,12 @@ def make_config(**kw):
 def build(force=False):
     """Compile the restatement and, where /root/reference exists, the tape-mode reference."""
     port = os.path.join(HERE, "_build", "librach_oracle.so")
-    src = os.path.join(HERE, "rach_oracle.c")
-    if force or not os.path.exists(port) or os.path.getmtime(port) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("rach_oracle.c", "rach_oracle_n.c", "ref_api.h")]
+    if force or not os.path.exists(port) or os.path.getmtime(port) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "_build/librach_oracle.so"],
                               stdout=subprocess.DEVNULL)
     have_ref = all(os.path.exists(os.path.join(HERE, "_ref", f))
-                   for f in ("libref_w.so", "libref_b.so"))
+                   for f in ("libref_w.so", "libref_b.so", "libref_n.so"))
     if os.path.isdir("/root/reference") and (force or not have_ref):
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
@@ -109,6 +109,42 @@ def run_ref(variant, cfg, per_ue=True, geom=False):
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     return _run(_lib(path, "ref_run"), cfg, per_ue, geom)
+
+
+N_DEFAULTS = dict(nGrantUL=2, maxRarWindow=5, maxMsg2TxCount=10, cellRadius=500.0, geometry=1)
+N_DUMP_FIELDS = ["timer", "active", "txTime", "firstTxTime", "secondTxTime", "nowBackoff", "preamble", "sector",
+                 "rarWindow", "msg1ReTx", "nTxPreamble", "msg2", "msg3Wait", "RA", "msg3Faile", "RaFailed"]
+
+
+def make_config_n(**kw):
+    """NOMA.c defaults (N:41-57): 2 grants per sector, maxRarWindow 5, maxMsg1ReTx 10, 500 m cell."""
+    d = dict(N_DEFAULTS)
+    d.update(kw)
+    return make_config(**d)
+
+
+def _run_n(f, cfg):
+    res = RefResult()
+    n = cfg.nUE
+    ue = np.zeros((n, 16), dtype=np.int32)
+    gain = np.zeros(n, dtype=np.float64)
+    rc = f(C.byref(cfg), C.byref(res), ue.ctypes.data_as(C.c_void_p), gain.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("oracle run failed rc=%d" % rc)
+    return res, ue, gain
+
+
+def run_ref_n(cfg):
+    """NOMA.c itself in tape mode -> (result, per-UE ints [n,16] in N_DUMP_FIELDS order, channelGain [n])."""
+    path = os.path.join(HERE, "_ref", "libref_n.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return _run_n(_lib(path, "ref_run"), cfg)
+
+
+def run_port_n(cfg):
+    build()
+    return _run_n(_lib(os.path.join(HERE, "_build", "librach_oracle.so"), "oracle_run_n"), cfg)
 
 
 def run_port(cfg, per_ue=True, geom=False):

@@ -34,6 +34,7 @@
 #include <stdarg.h>
 
 int   ref_tape_rand(int ue, int ms);
+int   ref_tape_rand_bs(int sector, int ms);
 void  ref_tape_srand(unsigned seed);
 void* ref_calloc_hook(size_t n, size_t sz);
 void  ref_free_hook(void* p);
