@@ -52,7 +52,7 @@ class RaOptions(C.Structure):
 
 
 SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_sim_run", "ra_sim_stats",
-           "ra_sim_stats_all", "ra_sim_dump_ues", "ra_sim_geometry", "ra_sim_kernel_ms",
+           "ra_sim_stats_all", "ra_sim_dump_ues", "ra_sim_geometry", "ra_sim_gains", "ra_sim_kernel_ms",
            "ra_sim_gpu_launches", "ra_sim_phase_cycles", "ra_sim_destroy", "ra_sim_last_error", "ra_params_default",
            "ra_horizon_ms", "ra_arrival_schedule", "ra_version"]
 
@@ -84,6 +84,7 @@ def load_lib():
     lib.ra_sim_stats_all.argtypes = [vp, vp]
     lib.ra_sim_dump_ues.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.ra_sim_geometry.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.ra_sim_gains.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.ra_sim_kernel_ms.restype = C.c_double
     lib.ra_sim_kernel_ms.argtypes = [vp]
     lib.ra_sim_gpu_launches.restype = C.c_longlong
@@ -102,9 +103,9 @@ def load_lib():
 
 
 def default_params(**kw):
-    """W defaults (RandomAccessWithNOMA.c:69-88) with overrides."""
+    """W defaults (RandomAccessWithNOMA.c:69-88) with overrides; variant=RA_VARIANT_N gives NOMA.c:41-57."""
     p = RaParams()
-    load_lib().ra_params_default(C.byref(p), RA_VARIANT_W)
+    load_lib().ra_params_default(C.byref(p), kw.get("variant", RA_VARIANT_W))
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)
@@ -166,6 +167,12 @@ class RachSim:
         n = self.points[point].nUE
         out = np.zeros((n, 6), dtype=np.float32)
         self._check(self._lib.ra_sim_geometry(self._h, point, rep, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def gains(self, point=0, rep=0):
+        n = self.points[point].nUE
+        out = np.zeros(n, dtype=np.float64)
+        self._check(self._lib.ra_sim_gains(self._h, point, rep, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def phase_cycles(self):

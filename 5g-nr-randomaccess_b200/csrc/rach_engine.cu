@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "rach_core.cuh"
+#include "rach_core_n.cuh"
 #include "rach_gpu.h"
 #include "rach_host.h"
 
@@ -38,7 +39,11 @@ struct RaKernelArgs {
     const RaPointDev* points;
     const int*        jobPoint;     /* [nJobs] point index                       */
     const unsigned*   jobRep;       /* [nJobs] tape replication id               */
-    const RaWork*     works;        /* [gridDim.x]                               */
+    const RaWork*     works;        /* [gridDim.x]  (variant W)                  */
+    const RaWorkN*    worksN;       /* [gridDim.x]  (variant N)                  */
+    float             cellRadius;   /* variant N (N:56)                          */
+    double*           gainDump;     /* [nJobs][cap] channelGain per UE (variant N, DUMP) or NULL */
+    size_t            gainStride;
     unsigned*         jobCounter;
     ra_stats*         stats;        /* [nJobs]                                   */
     int*              dump;         /* [nJobs][dumpStride] or NULL               */
@@ -187,6 +192,92 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Variant N (NOMA.c): one block per replication, phases of rach_core_n.cuh.
+ * ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ void rn_carve(RaSharedN& s, unsigned char* base, int R, int P) {
+    const size_t c = (size_t)RA_NSECT * P;
+    s.sLg = reinterpret_cast<double*>(base);     base += sizeof(double) * c;
+    s.sGain = reinterpret_cast<double*>(base);   base += sizeof(double) * c;
+    s.cnt = reinterpret_cast<unsigned*>(base);   base += sizeof(unsigned) * c;
+    s.who = reinterpret_cast<unsigned*>(base);   base += sizeof(unsigned) * c;
+    s.grant = reinterpret_cast<unsigned*>(base); base += sizeof(unsigned) * c;
+    s.sPos = reinterpret_cast<unsigned*>(base);  base += sizeof(unsigned) * c;
+    s.sIdx = reinterpret_cast<int*>(base);       base += sizeof(int) * c;
+    s.bcount = reinterpret_cast<unsigned*>(base); base += sizeof(unsigned) * (size_t)R;
+    s.m3count = reinterpret_cast<unsigned*>(base);
+}
+static size_t rn_smem_bytes(int R, int P) {
+    return (size_t)RA_NSECT * P * (2 * sizeof(double) + 5 * sizeof(unsigned)) + sizeof(unsigned) * ((size_t)R + RA_M3RING);
+}
+
+template <bool DUMP>
+__global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel_n(RaKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
+    __shared__ RaSharedN s;
+    __shared__ RaPointDev sPt;
+    __shared__ int sJob;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const RaWorkN w = a.worksN[blockIdx.x];
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sJob = (int)atomicAdd(a.jobCounter, 1u);
+        __syncthreads();
+        const int jobId = sJob;
+        if (jobId >= a.nJobs) break;
+        if (tid == 0) { sPt = a.points[a.jobPoint[jobId]]; rn_carve(s, ra_dyn_smem, sPt.R, sPt.P); }
+        __syncthreads();
+        const RaPointDev& pt = sPt;
+        RaJob job; job.pt = &pt; job.rep = a.jobRep[jobId];
+        job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
+        rn_job_init<DUMP>(job, s, tid, nt);
+        __syncthreads();
+        int simTime = pt.maxTime;
+        const unsigned Rm = (unsigned)(pt.R - 1);
+        for (int T = 0; T < pt.maxTime; ++T) {
+            if (T % pt.A == 0) {                                        /* a RACH occasion, N:668 */
+                rn_phaseA0(job, s, T, tid, nt);
+                __syncthreads();
+                for (unsigned i = tid; i < (unsigned)s.nArr; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i, a.cellRadius);
+                __syncthreads();
+                const unsigned nTx = s.bcount[(unsigned)T & Rm];
+                for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
+                __syncthreads();
+                if ((tid & 31) == 0 && (tid >> 5) < RA_NSECT) rn_phaseB_sector(job, w, s, T, tid >> 5);
+                __syncthreads();
+                for (unsigned j = tid; j < nTx; j += nt) rn_phaseC_item<DUMP>(job, w, s, T, j);
+                __syncthreads();
+                if (tid == 0) s.bcount[(unsigned)T & Rm] = 0;
+            }
+            const unsigned nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
+            if (nM3) {                                                  /* N:699 */
+                for (unsigned j = tid; j < nM3; j += nt) rn_msg3_item<DUMP>(job, w, s, T, j);
+                __syncthreads();
+                if (tid == 0) s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
+                __syncthreads();
+                if (s.nSuccess == (unsigned)pt.nUE) { simTime = T; break; }   /* N:707-710 */
+            }
+        }
+        __syncthreads();
+        const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
+        if (DUMP) {
+            rn_dump_inflight(job, w, s, last, tid, nt);
+            double* g = a.gainDump + (size_t)jobId * a.gainStride;
+            for (int i = tid; i < pt.nUE; i += nt) g[i] = i < s.activeCheck ? w.gain[i] : 0.0;
+        }
+        if (tid == 0) {
+            ra_stats st; memset(&st, 0, sizeof st);
+            st.simTimeMs = simTime; st.nSuccess = (int)s.nSuccess;
+            st.preambleTxSum = (long long)s.txSum; st.delaySum = (long long)s.delaySum;
+            st.continueFailed = (long long)s.nDropped;                  /* RaFailed UEs, N:483 */
+            st.finalSuccess = (long long)s.nSuccess;
+            st.updates = (long long)pt.nUE * (long long)((simTime + pt.A - 1) / pt.A);
+            a.stats[jobId] = st;
+            if (s.overflow) atomicExch(a.errFlag, s.overflow);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * activateUEs side outputs, RandomAccessWithNOMA.c:392-415, recomputed from the draw tape.
  * Types follow the C semantics of the reference: float locals, double libm calls.
  * ------------------------------------------------------------------------------------------ */
@@ -222,7 +313,8 @@ struct RaDev {
     RaPointDev* dPoints = nullptr;
     std::vector<int*> dArrCum;
     int* dJobPoint = nullptr; unsigned* dJobRep = nullptr; unsigned* dCounter = nullptr;
-    ra_stats* dStats = nullptr; RaWork* dWorks = nullptr; unsigned char* dWorkspace = nullptr;
+    ra_stats* dStats = nullptr; RaWork* dWorks = nullptr; RaWorkN* dWorksN = nullptr; unsigned char* dWorkspace = nullptr;
+    double* dGainDump = nullptr;
     int* dDump = nullptr; int* dErr = nullptr; float* dGeom = nullptr; ra_u64* dCyc = nullptr;
     int grid = 0; size_t smem = 0;
     cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -241,7 +333,7 @@ struct ra_sim {
     bool ran = false;
     double kernelMs = 0; long long launches = 0;
     size_t dumpStride = 0;
-    int maxP = 0, maxR = 0, cap = 0, cap3 = 0;
+    int maxP = 0, maxR = 0, cap = 0, cap3 = 0, variant = RA_VARIANT_W;
     std::string err;
 };
 
@@ -256,7 +348,7 @@ static void ra_free_dev(RaDev& d) {
     for (int* p : d.dArrCum) cudaFree(p);
     cudaFree(d.dPoints); cudaFree(d.dJobPoint); cudaFree(d.dJobRep); cudaFree(d.dCounter);
     cudaFree(d.dStats); cudaFree(d.dWorks); cudaFree(d.dWorkspace); cudaFree(d.dDump); cudaFree(d.dErr);
-    cudaFree(d.dGeom); cudaFree(d.dCyc);
+    cudaFree(d.dGeom); cudaFree(d.dCyc); cudaFree(d.dWorksN); cudaFree(d.dGainDump);
     if (d.e0) cudaEventDestroy(d.e0);
     if (d.e1) cudaEventDestroy(d.e1);
     if (d.stream) cudaStreamDestroy(d.stream);
@@ -306,29 +398,35 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     }
 
     /* grid and per-block workspace */
-    d.smem = ra_smem_bytes(sim->maxR, sim->maxP);
+    const bool isN = sim->variant == RA_VARIANT_N;
+    const bool dump = sim->opt.dumpUEs != 0;
+    d.smem = isN ? rn_smem_bytes(sim->maxR, sim->maxP) : ra_smem_bytes(sim->maxR, sim->maxP);
     if (d.smem > (size_t)prop.sharedMemPerBlockOptin) {
-        sim->err = "cohort tables (ring x preambles) exceed the shared memory of one block"; return RA_E_INVAL;
+        sim->err = "per-replication tables (ring x preambles) exceed the shared memory of one block"; return RA_E_INVAL;
     }
-    if (sim->opt.dumpUEs) RA_CUDA(sim, cudaFuncSetAttribute(ra_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
-    else RA_CUDA(sim, cudaFuncSetAttribute(ra_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
+    const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
+                           : (dump ? (const void*)ra_step_kernel<true> : (const void*)ra_step_kernel<false>);
+    RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
     int occ = 0;
-    if (sim->opt.dumpUEs) RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<true>, RA_NT, d.smem));
-    else RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ra_step_kernel<false>, RA_NT, d.smem));
+    RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RA_NT, d.smem));
     if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
     int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, RA_MINB);
+    if (isN && dump) {
+        cudaError_t e = cudaMalloc(&d.dGainDump, sizeof(double) * (size_t)sim->cap * (size_t)std::max(nJobs, 1));
+        if (e != cudaSuccess) { sim->err = "gain dump buffer does not fit on the device"; return RA_E_NOMEM; }
+    }
 
     const size_t cap = (size_t)sim->cap, cap3 = (size_t)sim->cap3;
     size_t off = 0;
     const size_t oBucket = off;    off = ra_align_up(off + sizeof(uint4) * cap * sim->maxR, 256);
     const size_t oMsg3 = off;      off = ra_align_up(off + sizeof(uint4) * cap3 * RA_M3RING, 256);
-    const size_t oLander = off;    off = ra_align_up(off + sizeof(uint4) * cap, 256);
-    const size_t oLMeta = off;     off = ra_align_up(off + sizeof(unsigned) * cap, 256);
-    const size_t oUnc = off;       off = ra_align_up(off + sizeof(uint4) * cap, 256);
-    const size_t oC3 = off;        off = ra_align_up(off + sizeof(uint4) * cap, 256);
-    const size_t oSingles = off;   off = ra_align_up(off + sizeof(unsigned) * cap, 256);
-    const size_t oE1 = off;        off = ra_align_up(off + sizeof(uint4) * cap3, 256);
-    const size_t oE1Meta = off;    off = ra_align_up(off + sizeof(unsigned) * cap3, 256);
+    const size_t oLander = off;    off = ra_align_up(off + sizeof(uint4) * cap, 256);               /* N: zombies */
+    const size_t oLMeta = off;     off = ra_align_up(off + (isN ? sizeof(double) : sizeof(unsigned)) * cap, 256);   /* N: gains */
+    const size_t oUnc = off;       if (!isN) off = ra_align_up(off + sizeof(uint4) * cap, 256);
+    const size_t oC3 = off;        if (!isN) off = ra_align_up(off + sizeof(uint4) * cap, 256);
+    const size_t oSingles = off;   if (!isN) off = ra_align_up(off + sizeof(unsigned) * cap, 256);
+    const size_t oE1 = off;        if (!isN) off = ra_align_up(off + sizeof(uint4) * cap3, 256);
+    const size_t oE1Meta = off;    if (!isN) off = ra_align_up(off + sizeof(unsigned) * cap3, 256);
     const size_t perBlock = off;
 
     size_t freeB = 0, totalB = 0;
@@ -341,6 +439,19 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     {
         cudaError_t e = cudaMalloc(&d.dWorkspace, perBlock * (size_t)grid);
         if (e != cudaSuccess) { sim->err = std::string("workspace cudaMalloc failed: ") + cudaGetErrorString(e); return RA_E_NOMEM; }
+    }
+    if (isN) {
+        std::vector<RaWorkN> worksN(grid);
+        for (int b = 0; b < grid; ++b) {
+            unsigned char* base = d.dWorkspace + perBlock * (size_t)b;
+            RaWorkN& w = worksN[b];
+            w.bucket = (uint4*)(base + oBucket); w.msg3 = (uint4*)(base + oMsg3);
+            w.zombie = (uint4*)(base + oLander); w.gain = (double*)(base + oLMeta);
+            w.cap = sim->cap; w.cap3 = sim->cap3;
+        }
+        RA_CUDA(sim, cudaMalloc(&d.dWorksN, sizeof(RaWorkN) * grid));
+        RA_CUDA(sim, cudaMemcpy(d.dWorksN, worksN.data(), sizeof(RaWorkN) * grid, cudaMemcpyHostToDevice));
+        return RA_OK;
     }
     std::vector<RaWork> works(grid);
     for (int b = 0; b < grid; ++b) {
@@ -378,6 +489,8 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
             g_createErr = std::string("point ") + std::to_string(i) + ": " + err; delete sim; return nullptr;
         }
         const ra_params& p = points[i];
+        if (i == 0) sim->variant = p.variant;
+        else if (p.variant != sim->variant) { g_createErr = "all points of one ra_sim must share the variant"; delete sim; return nullptr; }
         RaPointDev pt; memset(&pt, 0, sizeof pt);
         pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
         pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
@@ -389,7 +502,7 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         ra_host_arrcum(&p, sim->arrCum.back().data(), pt.nOcc);
         sim->maxP = std::max(sim->maxP, pt.P); sim->maxR = std::max(sim->maxR, pt.R);
         sim->cap = std::max(sim->cap, pt.nUE);
-        long long g2 = 2LL * std::min<long long>(pt.G, (long long)pt.nUE + 1) + 2;
+        long long g2 = (p.variant == RA_VARIANT_N ? 24LL : 2LL) * std::min<long long>(pt.G, (long long)pt.nUE + 1) + 4;
         sim->cap3 = std::max<long long>(sim->cap3, g2);
         sim->dumpStride = std::max(sim->dumpStride, (size_t)pt.nUE * RA_DUMP_W);
     }
@@ -441,7 +554,12 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = d.dCyc;
         a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
         RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
-        if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+        a.worksN = d.dWorksN; a.cellRadius = sim->points[0].cellRadius;
+        a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
+        if (sim->variant == RA_VARIANT_N) {
+            if (sim->opt.dumpUEs) ra_step_kernel_n<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+            else ra_step_kernel_n<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+        } else if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
         else ra_step_kernel<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
         RA_CUDA(sim, cudaGetLastError());
         RA_CUDA(sim, cudaEventRecord(d.e1, d.stream));
@@ -499,6 +617,7 @@ extern "C" int ra_sim_geometry(ra_sim* sim, int point, int rep, float* out) {
     if (!sim || !out) return RA_E_INVAL;
     if (!sim->ran) { sim->err = "ra_sim_geometry before ra_sim_run"; return RA_E_STATE; }
     if (point < 0 || point >= sim->nPoints || rep < 0 || rep >= sim->reps) { sim->err = "point/rep out of range"; return RA_E_INVAL; }
+    if (sim->variant != RA_VARIANT_W) { sim->err = "ra_sim_geometry is for variant W; variant N reports ra_sim_gains"; return RA_E_STATE; }
     if (!sim->points[point].geometry) { sim->err = "ra_sim_geometry needs geometry = 1 (variant B draws no positions)"; return RA_E_STATE; }
     RaDev& d = sim->devs[0];
     RA_CUDA(sim, cudaSetDevice(d.id));
@@ -528,6 +647,19 @@ extern "C" int ra_sim_phase_cycles(ra_sim* sim, unsigned long long* out10) {
         RA_CUDA(sim, cudaMemcpy(h, d.dCyc, sizeof h, cudaMemcpyDeviceToHost));
         for (int k = 0; k < RA_NPHASE; ++k) out10[k] += h[k];
     }
+    return RA_OK;
+}
+
+extern "C" int ra_sim_gains(ra_sim* sim, int point, int rep, double* out) {
+    if (!sim || !out) return RA_E_INVAL;
+    if (!sim->ran) { sim->err = "ra_sim_gains before ra_sim_run"; return RA_E_STATE; }
+    if (sim->variant != RA_VARIANT_N || !sim->opt.dumpUEs) { sim->err = "ra_sim_gains needs variant N and ra_options.dumpUEs = 1"; return RA_E_STATE; }
+    if (point < 0 || point >= sim->nPoints || rep < 0 || rep >= sim->reps) { sim->err = "point/rep out of range"; return RA_E_INVAL; }
+    const int job = point * sim->reps + rep;
+    RaDev& d = sim->devs[sim->jobDev[job]];
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    RA_CUDA(sim, cudaMemcpy(out, d.dGainDump + (size_t)sim->jobLocal[job] * (size_t)sim->cap,
+                            sizeof(double) * (size_t)sim->points[point].nUE, cudaMemcpyDeviceToHost));
     return RA_OK;
 }
 

@@ -40,6 +40,9 @@ extern "C" int ra_params_default(ra_params* p, int variant) {
     p->hUT = 1.8;                   /* W:82 */
     p->geometry = 1;
     p->seed = 0;
+    if (variant == RA_VARIANT_N) {     /* NOMA.c:41-57 */
+        p->nGrantUL = 2; p->maxRarWindow = 5; p->maxMsg2TxCount = 10; p->cellRadius = 500;
+    }
     return RA_OK;
 }
 
@@ -85,12 +88,19 @@ static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
 #define RA_BAD(...) do { snprintf(err, errLen, __VA_ARGS__); return RA_E_INVAL; } while (0)
-    if (p->variant != RA_VARIANT_W) RA_BAD("variant %d is not built (only RA_VARIANT_W = W/B dynamics)", p->variant);
+    if (p->variant != RA_VARIANT_W && p->variant != RA_VARIANT_N)
+        RA_BAD("variant %d is not built (RA_VARIANT_W = W/B dynamics, RA_VARIANT_N = NOMA.c)", p->variant);
+    if (p->variant == RA_VARIANT_N) {
+        /* NOMA.c: Beta traffic only (N:675), rarWindow = 5 >= maxRarWindow is the only path that retransmits (N:453-455) */
+        if (p->distribution == 1) RA_BAD("variant N has Beta traffic only (NOMA.c:675)");
+        if (p->maxRarWindow > 5) RA_BAD("variant N: maxRarWindow %d > 5 never retransmits in NOMA.c:453-455; not supported", p->maxRarWindow);
+        if (p->maxMsg2TxCount < 1) RA_BAD("variant N: maxMsg2TxCount carries maxMsg1ReTx (NOMA.c:46) and must be >= 1");
+    }
     if (p->nUE < 1 || p->nUE > (1 << 24)) RA_BAD("nUE %d out of range [1, 2^24]", p->nUE);
     if (p->nPreamble < 1 || p->nPreamble > 256) RA_BAD("nPreamble %d out of range [1, 256]", p->nPreamble);
     if (p->backoffIndicator < 1 || p->backoffIndicator > 4096) RA_BAD("backoffIndicator %d out of range [1, 4096]", p->backoffIndicator);
     if (p->nGrantUL < 1) RA_BAD("nGrantUL %d must be >= 1", p->nGrantUL);
-    if (p->maxRarWindow < 2 || p->maxRarWindow > 256) RA_BAD("maxRarWindow %d out of range [2, 256] (RAR window 1..255)", p->maxRarWindow);
+    if (p->variant == RA_VARIANT_W && (p->maxRarWindow < 2 || p->maxRarWindow > 256)) RA_BAD("maxRarWindow %d out of range [2, 256] (RAR window 1..255)", p->maxRarWindow);
     if (p->maxMsg2TxCount < 0 || p->maxMsg2TxCount > 255) RA_BAD("maxMsg2TxCount %d out of range [0, 255] (max retx 1..256)", p->maxMsg2TxCount);
     if (p->accessTime < 1 || p->accessTime > 4096) RA_BAD("accessTime %d out of range [1, 4096]", p->accessTime);
     const int h = ra_horizon_ms(p);
@@ -101,6 +111,7 @@ int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
 
 int ra_host_ring(const ra_params* p) {
     const int a = p->accessTime > 5 ? p->accessTime : 5;
+    if (p->variant == RA_VARIANT_N) return next_pow2(p->backoffIndicator + a + 6);   /* occasion <= T + BI + A + 2 */
     return next_pow2(p->backoffIndicator + a + p->maxRarWindow + 2);
 }
 

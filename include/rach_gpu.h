@@ -39,7 +39,9 @@ extern "C" {
 
 #define RA_VARIANT_W  0   /* RandomAccessWithNOMA.c / RandomAccessSimulatorBeta.c dynamics */
 #define RA_VARIANT_U0 1   /* RandomAccessSimulator.c legacy dynamics   (not built yet)     */
-#define RA_VARIANT_N  2   /* NOMA.c sector / gain-pairing dynamics      (not built yet)     */
+#define RA_VARIANT_N  2   /* NOMA.c sector / gain-pairing dynamics (N:131-324, 449-566, 665-711):
+                             nGrantUL = grants per sector (N:43), maxRarWindow <= 5 (N:45),
+                             maxMsg2TxCount carries maxMsg1ReTx (N:46), cellRadius (N:56), Beta only */
 
 #define RA_OK            0
 #define RA_E_INVAL      -1   /* bad argument / unsupported parameter value */
@@ -117,6 +119,10 @@ int         ra_sim_dump_ues(ra_sim* sim, int point, int rep, int* out);
 /* out[nUE * 6] floats: angle, xCoordinate, yCoordinate, distance, channelGain, (float)sector
  * (W:396-415).  Requires geometry=1. */
 int         ra_sim_geometry(ra_sim* sim, int point, int rep, float* out);
+/* variant N with dumpUEs: out[nUE] doubles = channelGain (N:183-191), 0 for UEs that never arrived;
+ * ra_sim_dump_ues then writes: timer active txTime firstTxTime secondTxTime nowBackoff preamble sector
+ * rarWindow msg1ReTx nTxPreamble msg2 msg3Wait RA msg3Faile RaFailed (saveResultLogs order, N:577-592) */
+int         ra_sim_gains(ra_sim* sim, int point, int rep, double* out);
 double      ra_sim_kernel_ms(const ra_sim* sim);     /* device time of the last run (max over devices) */
 long long   ra_sim_gpu_launches(const ra_sim* sim);  /* kernels launched by the last run */
 /* profiling aid: cycles spent per engine phase by thread 0 of every block, summed (out[10]) */

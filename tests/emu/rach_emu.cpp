@@ -106,3 +106,79 @@ extern "C" int emu_run(const ref_config* cfg, ref_result* res, int* perUE, float
     res->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Variant N: the phases of rach_core_n.cuh, same emulation scheme.
+ * perUE: nUE*16 ints in N dump order; geom: nUE doubles (channelGain).
+ * ------------------------------------------------------------------------------------------ */
+#include "rach_core_n.cuh"
+
+template <bool DUMP>
+static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, double* gains, int NT) {
+    ra_params p; ra_params_default(&p, RA_VARIANT_N);
+    p.nUE = cfg->nUE; p.distribution = 2; p.nPreamble = cfg->nPreamble;
+    p.backoffIndicator = cfg->backoffIndicator; p.nGrantUL = cfg->nGrantUL;
+    p.maxRarWindow = cfg->maxRarWindow; p.maxMsg2TxCount = cfg->maxMsg2TxCount;
+    p.accessTime = cfg->accessTime; p.cellRadius = cfg->cellRadius; p.seed = cfg->seed;
+    char err[256];
+    if (ra_host_validate(&p, err, sizeof err) != RA_OK) { fprintf(stderr, "emu: %s\n", err); return -1; }
+    RaPointDev pt; memset(&pt, 0, sizeof pt);
+    pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
+    pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
+    pt.maxTime = ra_horizon_ms(&p); pt.geometry = 1; pt.R = ra_host_ring(&p);
+    pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed;
+    ra_host_fill_point(&pt);
+    std::vector<int> arrCum(pt.nOcc);
+    ra_host_arrcum(&p, arrCum.data(), pt.nOcc);
+    pt.arrCum = arrCum.data();
+
+    RaWorkN w; w.cap = pt.nUE;
+    long long g2 = 24LL * (pt.G < pt.nUE + 1 ? pt.G : pt.nUE + 1) + 4; w.cap3 = (int)g2;
+    std::vector<uint4> bucket((size_t)pt.R * w.cap), msg3((size_t)RA_M3RING * w.cap3), zombie(w.cap);
+    std::vector<double> gain(w.cap);
+    w.bucket = bucket.data(); w.msg3 = msg3.data(); w.zombie = zombie.data(); w.gain = gain.data();
+    const size_t c = (size_t)RA_NSECT * pt.P;
+    std::vector<unsigned> cnt(c), who(c), grant(c), sPos(c), bcount(pt.R), m3count(RA_M3RING);
+    std::vector<int> sIdx(c);
+    std::vector<double> sLg(c), sGain(c);
+    RaSharedN s; memset(&s, 0, sizeof s);
+    s.cnt = cnt.data(); s.who = who.data(); s.grant = grant.data(); s.sPos = sPos.data(); s.sIdx = sIdx.data();
+    s.sLg = sLg.data(); s.sGain = sGain.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
+    RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
+
+    for (int t = 0; t < NT; ++t) rn_job_init<DUMP>(job, s, t, NT);
+    int simTime = pt.maxTime;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    for (int T = 0; T < pt.maxTime; ++T) {
+        if (T % pt.A == 0) {
+            for (int t = 0; t < NT; ++t) rn_phaseA0(job, s, T, t, NT);
+            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, i, p.cellRadius);
+            const unsigned nTx = s.bcount[(unsigned)T & Rm];
+            for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseA2_item(pt, w, s, T, j);
+            for (int sec = 0; sec < RA_NSECT; ++sec) rn_phaseB_sector(job, w, s, T, sec);
+            for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseC_item<DUMP>(job, w, s, T, j);
+            s.bcount[(unsigned)T & Rm] = 0;
+        }
+        const unsigned nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
+        if (nM3) {
+            for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nM3; j += NT) rn_msg3_item<DUMP>(job, w, s, T, j);
+            s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
+            if (s.nSuccess == (unsigned)pt.nUE) { simTime = T; break; }
+        }
+        if (s.overflow) { fprintf(stderr, "emu N: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
+    }
+    const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
+    if (DUMP) {
+        for (int t = 0; t < NT; ++t) rn_dump_inflight(job, w, s, last, t, NT);
+        if (gains) for (int i = 0; i < pt.nUE; ++i) gains[i] = i < s.activeCheck ? w.gain[i] : 0.0;
+    }
+    memset(res, 0, sizeof *res);
+    res->simTimeMs = simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
+    res->delaySum = (long long)s.delaySum; res->continueFailed = (long long)s.nDropped; res->captured = 1;
+    return 0;
+}
+
+extern "C" int emu_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom) {
+    return perUE ? emu_run_n_t<true>(cfg, res, perUE, (double*)geom, emu_threads)
+                 : emu_run_n_t<false>(cfg, res, NULL, NULL, emu_threads);
+}

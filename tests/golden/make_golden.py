@@ -49,6 +49,15 @@ CASES = [
     ("b_g12_20000", "b", dict(B, nUE=20000, nGrantUL=12, seed=5)),
 ]
 
+N_CASES = [
+    ("n_default_3000", dict(nUE=3000)),
+    ("n_default_10000", dict(nUE=10000, seed=1)),                      # NOMA.c as shipped: 98.9 %
+    ("n_default_30000", dict(nUE=30000, seed=2)),                      # 73.4 %
+    ("n_g1_p8_4000", dict(nUE=4000, nGrantUL=1, nPreamble=8, seed=3)),
+    ("n_g4_bi40_sub10_8000", dict(nUE=8000, nGrantUL=4, backoffIndicator=40, accessTime=10, seed=4)),
+    ("n_retx3_r100_6000", dict(nUE=6000, maxMsg2TxCount=3, cellRadius=100.0, seed=5)),
+]
+
 STAT_KEYS = ["simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "failCountSum",
              "continueFailed", "collisionPreambles", "totalPreambleTxop", "collisionScans",
              "totalScans", "draws", "maxDrawsPerUeMs", "nAccessUE", "averageDelay",
@@ -71,6 +80,18 @@ def main():
         if cfg.nUE <= 3000:
             ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
         print("%-28s %s" % (name, {k: d[k] for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum")}))
+    for name, kw in N_CASES:
+        cfg = O.make_config_n(**kw)
+        res, ue, gain = O.run_ref_n(cfg)
+        full = dict(O.DEFAULTS); full.update(O.N_DEFAULTS); full.update(kw)
+        stats[name] = {"variant": "n", "config": full,
+                       "stats": {k: getattr(res, k) for k in ("nSuccess", "preambleTxSum", "delaySum", "draws", "maxDrawsPerUeMs")},
+                       "ue_sha256": hashlib.sha256(np.ascontiguousarray(ue).tobytes()).hexdigest(),
+                       "gain_sha256": hashlib.sha256(np.ascontiguousarray(gain).tobytes()).hexdigest(),
+                       "dropped": int((ue[:, 15] > 0).sum())}
+        if cfg.nUE <= 3000:
+            ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
+        print("%-28s %s" % (name, stats[name]["stats"]))
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "golden_stats.json"), "w") as f:
         json.dump(stats, f, indent=1, sort_keys=True)

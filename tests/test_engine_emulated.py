@@ -70,3 +70,28 @@ def test_fuzz(oracle, emu):
                   geometry=rnd.choice([0, 1]), stopMs=rnd.choice([0, 0, 0, 777, 3001]))
         late += _cmp(oracle, emu, kw, threads=rnd.choice([1, 3, 32, 64, 256])).lateAbsorbed
     assert late > 0
+
+
+def test_noma_variant_emulated(oracle, emu):
+    """Variant N phases (rach_core_n.cuh) on the host against the N oracle, incl. fp64 gains."""
+    so = os.path.join(ROOT, "tests", "emu", "_build", "librach_emu.so")
+    f = oracle._lib(so, "emu_run_n")
+    rnd = random.Random(31)
+    cases = [dict(nUE=2000), dict(nUE=20000, seed=4)]
+    for _ in range(40):
+        cases.append(dict(nUE=rnd.choice([1, 5, 300, 3000, 9000]), nPreamble=rnd.choice([1, 3, 54, 64]),
+                          backoffIndicator=rnd.choice([1, 2, 20, 40]), nGrantUL=rnd.choice([1, 2, 4, 12]),
+                          maxMsg2TxCount=rnd.choice([1, 3, 10]), accessTime=rnd.choice([5, 5, 6, 10]),
+                          maxRarWindow=rnd.choice([3, 5]), cellRadius=rnd.choice([100.0, 500.0]),
+                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000)))
+    zomb = 0
+    for kw in cases:
+        cfg = oracle.make_config_n(**kw)
+        p, ue, g = oracle.run_port_n(cfg)
+        e, ue2, g2 = oracle._run_n(f, cfg)
+        for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum"):
+            assert getattr(p, k) == getattr(e, k), (k, kw)
+        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+        np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
+        zomb += int(((ue[:, 1] == 1) & (ue[:, 14] > 0) & (ue[:, 15] == 0) & (ue[:, 2] < p.simTimeMs - 100)).sum())
+    assert zomb > 0      # restarts that can never transmit again (NOMA.c:538 + :692) were exercised

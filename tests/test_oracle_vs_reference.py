@@ -1,6 +1,7 @@
 """The C restatement against the reference sources THEMSELVES (tape-mode build under
 oracle/_ref).  Runs wherever oracle/_ref/libref_*.so exists (built here from /root/reference;
 the prebuilt files travel to the GPU box)."""
+import os
 import random
 
 import numpy as np
@@ -60,3 +61,25 @@ def test_fuzz_parameters(oracle):
                   cellRadius=rnd.choice([400.0, 777.5]))
         late += _compare(oracle, variant, kw)["lateRestarts"]
     assert late > 0     # the Msg3-restart-lands-on-this-ms corner was exercised
+
+
+def test_noma_variant_against_noma_c(oracle):
+    """rach_oracle_n.c against NOMA.c itself in tape mode: 16 ints and the fp64 channelGain of every UE."""
+    if not os.path.exists(os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_n.so")):
+        pytest.skip("oracle/_ref/libref_n.so not built")
+    rnd = random.Random(99)
+    cases = [dict(nUE=2000), dict(nUE=12000, seed=3, rep=2)]
+    for _ in range(25):
+        cases.append(dict(nUE=rnd.choice([1, 5, 300, 3000, 8000]), nPreamble=rnd.choice([1, 3, 54, 64]),
+                          backoffIndicator=rnd.choice([1, 2, 20, 40]), nGrantUL=rnd.choice([1, 2, 4, 12]),
+                          maxMsg2TxCount=rnd.choice([1, 3, 10]), accessTime=rnd.choice([5, 5, 6, 10]),
+                          maxRarWindow=rnd.choice([3, 5]), cellRadius=rnd.choice([100.0, 500.0]),
+                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000)))
+    for kw in cases:
+        cfg = oracle.make_config_n(**kw)
+        r, ue, g = oracle.run_ref_n(cfg)
+        p, ue2, g2 = oracle.run_port_n(cfg)
+        for k in ("nSuccess", "preambleTxSum", "delaySum", "draws", "maxDrawsPerUeMs"):
+            assert getattr(r, k) == getattr(p, k), (k, kw)
+        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+        np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
