@@ -40,7 +40,9 @@ def test_readme_tables(retx):
                                 ("delay ms", delay, README[retx][n][2])):
             mean, sd = ours.mean(), ours.std(ddof=1)
             # our standard error + the published mean's own (100 seeds, same spread) ; 4 sigma
-            tol = 4.0 * sd * np.sqrt(1.0 / reps + 1.0 / 100.0) + 0.002 * abs(pub) + 1e-9
+            # (the retx-50 table is visibly noisier than 100 seeds would give -- 24.671 @60k vs 24.631 @70k -- so
+            #  never tighter than 1 % of the published figure)
+            tol = max(4.0 * sd * np.sqrt(1.0 / reps + 1.0 / 100.0) + 0.002 * abs(pub), 0.01 * abs(pub)) + 1e-9
             if n == 10000:
                 # the README contradicts itself at 10 000 UEs, where the limit is never reached and the three
                 # tables should agree: tx 2.59 / 2.561 / 3.541, delay 47.1 / 45.4 / 58.8 -> 5 % is all it pins
