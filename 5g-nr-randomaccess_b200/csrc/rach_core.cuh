@@ -183,7 +183,7 @@ RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const
     ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
     RA_AADD(&s.cnt[c], 1u);
-    RA_AMIN(&s.minI[c], rec.x);
+    if (rec.x < s.minI[c]) RA_AMIN(&s.minI[c], rec.x);   /* plain read first: the minimum rarely moves */
 }
 
 /* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old

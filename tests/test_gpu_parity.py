@@ -224,3 +224,22 @@ def test_noma_batch(pkg, oracle):
     for rep in (0, 13, 39):
         res, _, _ = oracle.run_port_n(oracle.make_config_n(nUE=4000, seed=12, rep=7 + rep))
         assert int(st[0, rep]["nSuccess"]) == res.nSuccess and int(st[0, rep]["delaySum"]) == res.delaySum
+
+
+def test_multi_device_in_one_process(pkg):
+    """ra_sim_create(devices[]) shards one job list over several GPUs from a single host thread;
+    results equal the single-device run (skipped on a 1-GPU box)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pa = pkg.default_params(nUE=5000, seed=5)
+    pb = pkg.default_params(nUE=2000, seed=6, nGrantUL=3)
+    with pkg.RachSim([pa, pb], reps=16, devices=[0]) as sim:
+        sim.run()
+        one = sim.stats_all()
+    with pkg.RachSim([pa, pb], reps=16, devices=[0, 1], dump_ues=True) as sim:
+        sim.run()
+        two = sim.stats_all()
+        ue = sim.dump_ues(1, 15)
+    assert (one == two).all()
+    assert ue.shape == (2000, 16) and (ue[:, 13] == 1).sum() == int(two[1, 15]["nSuccess"])
