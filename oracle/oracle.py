@@ -62,12 +62,12 @@ def make_config(**kw):
 def build(force=False):
     """Compile the restatement and, where /root/reference exists, the tape-mode reference."""
     port = os.path.join(HERE, "_build", "librach_oracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("rach_oracle.c", "rach_oracle_n.c", "ref_api.h")]
+    srcs = [os.path.join(HERE, f) for f in ("rach_oracle.c", "rach_oracle_n.c", "rach_oracle_u0.c", "ref_api.h")]
     if force or not os.path.exists(port) or os.path.getmtime(port) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", HERE, "_build/librach_oracle.so"],
                               stdout=subprocess.DEVNULL)
     have_ref = all(os.path.exists(os.path.join(HERE, "_ref", f))
-                   for f in ("libref_w.so", "libref_b.so", "libref_n.so"))
+                   for f in ("libref_w.so", "libref_b.so", "libref_n.so", "libref_u0.so"))
     if os.path.isdir("/root/reference") and (force or not have_ref):
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
@@ -145,6 +145,32 @@ def run_ref_n(cfg):
 def run_port_n(cfg):
     build()
     return _run_n(_lib(os.path.join(HERE, "_build", "librach_oracle.so"), "oracle_run_n"), cfg)
+
+
+U0_DEFAULTS = dict(nPreamble=64, distribution=1, geometry=0)
+U0_DUMP_FIELDS = ["timer", "active", "txTime", "preamble", "preambleChange", "rarWindow", "maxRarCounter",
+                  "preambleTxCounter", "msg2Flag", "connectionRequest", "msg4Flag", "raFailed", "nowBackoff", "-", "-", "-"]
+
+
+def make_config_u0(**kw):
+    """RandomAccessSimulator.c as shipped (U0:48-59): 64 preambles, BI 20, Uniform 60 s."""
+    d = dict(U0_DEFAULTS)
+    d.update(kw)
+    return make_config(**d)
+
+
+def run_ref_u0(cfg):
+    path = os.path.join(HERE, "_ref", "libref_u0.so")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    r, ue, _ = _run(_lib(path, "ref_run"), cfg, True, False)
+    return r, ue
+
+
+def run_port_u0(cfg):
+    build()
+    r, ue, _ = _run(_lib(os.path.join(HERE, "_build", "librach_oracle.so"), "oracle_run_u0"), cfg, True, False)
+    return r, ue
 
 
 def run_port(cfg, per_ue=True, geom=False):
