@@ -1,0 +1,135 @@
+/*
+ * rach_core_u0.cuh -- variant U0: the oldest simulator, RandomAccessSimulator.c (main loop
+ * U0:75-126, selectPreamble U0:157-197, preambleCollision U0:200-233,
+ * requestResourceAllocation U0:235-257, timerIncrease U0:259-266).
+ *
+ * U0 has index-order effects that differ from W (the group update of U0:228-229 makes the
+ * members above the scanner back off in the same ms and the scanner one ms later; UEs in the
+ * Msg3 phase scan too, U0:107; dropped UEs keep colliding, U0:207 has no raFailed test), a
+ * 60 s Uniform horizon and a live set of a few dozen UEs.  It is run here the simple exact way:
+ * ONE THREAD PER REPLICATION walks the ms loop over a compact, index-ordered list of the live
+ * UEs (arrived, not finished; dropped UEs stay as "phantoms") and performs the reference's own
+ * steps on it -- the O(nUE) loops of the reference shrink to O(live).  Replications are
+ * independent, so a launch runs thousands of them side by side.  Not tuned (secondary variant).
+ */
+#ifndef RACH_CORE_U0_CUH
+#define RACH_CORE_U0_CUH
+
+#include "rach_core.cuh"
+
+struct RuUE {            /* 64 bytes */
+    int idx, timer, active, txTime, preamble, rarWindow, maxRarCounter, preambleTxCounter;
+    int msg2Flag, connectionRequest, msg4Flag, preambleChange, raFailed, nowBackoff, pad0, pad1;
+};
+
+struct RuStats { int simTime, nSuccess; long long txSum, delaySum, collisionPreambles, totalPreambleTxop, dropped; int overflow; };
+
+/* dump row: timer active txTime preamble preambleChange rarWindow maxRarCounter preambleTxCounter
+ * msg2Flag connectionRequest msg4Flag raFailed nowBackoff 0 0 0 (saveResult order, U0:339-341) */
+RA_HD void ru_dump_row(int* o, const RuUE& u) {
+    o[0] = u.timer; o[1] = u.active; o[2] = u.txTime; o[3] = u.preamble; o[4] = u.preambleChange;
+    o[5] = u.rarWindow; o[6] = u.maxRarCounter; o[7] = u.preambleTxCounter; o[8] = u.msg2Flag;
+    o[9] = u.connectionRequest; o[10] = u.msg4Flag; o[11] = u.raFailed; o[12] = u.nowBackoff;
+    o[13] = 0; o[14] = 0; o[15] = 0;
+}
+
+template <bool DUMP>
+RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* out) {
+    const RaPointDev& pt = *job.pt;
+    const int nUE = pt.nUE, P = pt.P, BI = pt.BI, maxTime = pt.maxTime, accessTime = 5;   /* U0:57,59 */
+    const int nAccessUE = pt.G;                       /* host: ceil(n*5/60000), at least 1 (U0:60-64) */
+    RuStats st; st.simTime = maxTime; st.nSuccess = 0; st.txSum = st.delaySum = 0;
+    st.collisionPreambles = st.totalPreambleTxop = st.dropped = 0; st.overflow = 0;
+    if (DUMP) for (int i = 0; i < nUE; ++i) {         /* calloc + initialUE, U0:46,149-155 */
+        int* o = job.dump + (size_t)i * RA_DUMP_W;
+        for (int k = 0; k < RA_DUMP_W; ++k) o[k] = 0;
+        o[0] = -1; o[1] = -1; o[2] = -1; o[3] = -1;
+    }
+    int nLive = 0, nDead = 0, activeCheck = 0, arrived = 0, time;
+    for (time = 0; time < maxTime; time++) {
+        if (time % accessTime == 1) {                 /* U0:77-94 (bound fixed: i < nUE) */
+            if (activeCheck >= nUE) activeCheck = nUE; else activeCheck += nAccessUE;
+            int upto = activeCheck + 1 < nUE ? activeCheck + 1 : nUE;
+            for (; arrived < upto; ++arrived) {
+                if (nLive >= cap) { st.overflow = 1; break; }
+                RuUE u; u.idx = arrived; u.timer = 0; u.active = 1; u.txTime = time + 1; u.preamble = -1;
+                u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter = 0; u.msg2Flag = 0;
+                u.connectionRequest = 0; u.msg4Flag = 0; u.preambleChange = 0; u.raFailed = 0; u.nowBackoff = 0;
+                u.pad0 = u.pad1 = 0;
+                live[nLive++] = u;
+            }
+        }
+        for (int a = 0; a < nLive; ++a) {
+            RuUE u = live[a];
+            if (!(u.msg4Flag == 0 && u.raFailed != -1)) continue;            /* U0:99 */
+            unsigned k = 0;
+            if (u.active == 1 && u.msg2Flag == 0) {                           /* selectPreamble U0:157-197 */
+                if (u.preamble == -1) {
+                    u.preamble = (int)ra_mod((unsigned)rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE), (unsigned)P, pt.magicP);
+                    u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter = 0; u.preambleChange = 1;
+                } else if (u.nowBackoff == 0) {
+                    u.rarWindow++;
+                    if (u.rarWindow >= 5) {
+                        int tmp = (int)ra_mod((unsigned)rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE), (unsigned)BI, pt.magicBI) + 2;
+                        u.txTime = time + tmp; u.nowBackoff = tmp; u.rarWindow = 0; u.maxRarCounter++;
+                        if (u.maxRarCounter >= 10) {
+                            u.raFailed = -1; st.dropped++;
+                            u.preamble = (int)ra_mod((unsigned)rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE), (unsigned)P, pt.magicP);
+                            u.maxRarCounter = 0; u.preambleChange++;
+                        }
+                    }
+                }
+            }
+            live[a] = u;                                                      /* the scan below reads the list */
+            if (u.txTime + 2 == time && u.txTime != -1) {                     /* preambleCollision U0:107-110, 200-233 */
+                int check = 0;
+                for (int b = 0; b < nLive; ++b)
+                    if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
+                if (check == 1) {
+                    st.totalPreambleTxop++;
+                    u.preambleTxCounter++; u.active = 2; u.txTime = time + 2; u.connectionRequest = 0; u.msg2Flag = 1;
+                } else {
+                    st.collisionPreambles += check;
+                    for (int b = 0; b < nLive; ++b)
+                        if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
+                            live[b].rarWindow = 5; live[b].txTime = time + 3;
+                        }
+                    u = live[a];                                              /* the scanner may be a member */
+                }
+            }
+            if (u.active == 2 && u.txTime + 2 == time) {                      /* requestResourceAllocation U0:113-115, 235-257 */
+                u.connectionRequest++;
+                if (u.connectionRequest < 48) {
+                    int r = rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE);
+                    if (rach_msg3_success(r)) { u.msg4Flag = 1; u.active = 0; st.nSuccess++; }
+                    else u.txTime = time + 1;
+                } else {
+                    u.active = 1;
+                    u.txTime = time + (int)ra_mod((unsigned)rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE), (unsigned)BI, pt.magicBI) + 2;
+                    u.preamble = (int)ra_mod((unsigned)rach_tape_rand31(pt.seed, job.rep, (unsigned)u.idx, (unsigned)time, k++, RACH_TAPE_TAG_UE), (unsigned)P, pt.magicP);
+                    u.msg2Flag = 0; u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter++;
+                }
+            }
+            if (u.active > 0 && u.msg4Flag == 0) {                            /* U0:118-119, 259-266 */
+                u.timer++;
+                if (u.nowBackoff != 0) u.nowBackoff--;
+            }
+            live[a] = u;
+            if (u.msg4Flag == 1) {
+                st.txSum += u.preambleTxCounter; st.delaySum += u.timer; nDead++;
+                if (DUMP) ru_dump_row(job.dump + (size_t)u.idx * RA_DUMP_W, u);
+            }
+        }
+        if (st.nSuccess == nUE) break;                                        /* U0:122-125 */
+        if (nDead > 16 && nDead * 4 > nLive) {                                /* drop the finished ones, keep index order */
+            int w = 0;
+            for (int a = 0; a < nLive; ++a) if (live[a].msg4Flag == 0) { if (w != a) live[w] = live[a]; ++w; }
+            nLive = w; nDead = 0;
+        }
+    }
+    st.simTime = time;
+    if (DUMP) for (int a = 0; a < nLive; ++a) if (live[a].msg4Flag == 0) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
+    *out = st;
+}
+
+#endif /* RACH_CORE_U0_CUH */

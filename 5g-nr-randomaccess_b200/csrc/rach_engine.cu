@@ -23,6 +23,7 @@
 
 #include "rach_core.cuh"
 #include "rach_core_n.cuh"
+#include "rach_core_u0.cuh"
 #include "rach_gpu.h"
 #include "rach_host.h"
 
@@ -43,6 +44,7 @@ struct RaKernelArgs {
     const RaWorkN*    worksN;       /* [gridDim.x]  (variant N)                  */
     float             cellRadius;   /* variant N (N:56)                          */
     double*           gainDump;     /* [nJobs][cap] channelGain per UE (variant N, DUMP) or NULL */
+    RuUE*             liveBase;     /* [threads][cap] live lists (variant U0)    */
     size_t            gainStride;
     unsigned*         jobCounter;
     ra_stats*         stats;        /* [nJobs]                                   */
@@ -278,6 +280,31 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel_n(RaKernelArgs 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Variant U0 (RandomAccessSimulator.c): one THREAD per replication (rach_core_u0.cuh).
+ * ------------------------------------------------------------------------------------------ */
+template <bool DUMP>
+__global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    RuUE* live = a.liveBase + (size_t)gtid * (size_t)cap;
+    for (;;) {
+        const int jobId = (int)atomicAdd(a.jobCounter, 1u);
+        if (jobId >= a.nJobs) break;
+        const RaPointDev* pt = &a.points[a.jobPoint[jobId]];
+        RaJob job; job.pt = pt; job.rep = a.jobRep[jobId];
+        job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
+        RuStats st;
+        ru_run_replication<DUMP>(job, live, cap, &st);
+        ra_stats o; memset(&o, 0, sizeof o);
+        o.simTimeMs = st.simTime; o.nSuccess = st.nSuccess; o.preambleTxSum = st.txSum; o.delaySum = st.delaySum;
+        o.continueFailed = st.dropped; o.finalSuccess = st.nSuccess;
+        o.collisionPreambles = st.collisionPreambles; o.totalPreambleTxop = st.totalPreambleTxop;
+        o.updates = (long long)pt->nUE * (long long)((st.simTime + 4) / 5);
+        a.stats[jobId] = o;
+        if (st.overflow) atomicExch(a.errFlag, st.overflow);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * activateUEs side outputs, RandomAccessWithNOMA.c:392-415, recomputed from the draw tape.
  * Types follow the C semantics of the reference: float locals, double libm calls.
  * ------------------------------------------------------------------------------------------ */
@@ -397,6 +424,20 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
         if (e != cudaSuccess) { sim->err = "dump buffer does not fit on the device (dumpUEs keeps nUE*16 ints per replication)"; return RA_E_NOMEM; }
     }
 
+    if (sim->variant == RA_VARIANT_U0) {
+        /* one thread per replication, 32 threads per block; live list of cap UEs (64 B each) per thread */
+        size_t freeB = 0, totalB = 0;
+        RA_CUDA(sim, cudaMemGetInfo(&freeB, &totalB));
+        const size_t perThread = sizeof(RuUE) * (size_t)sim->cap;
+        long long threads = std::min<long long>(nJobs, (long long)((double)freeB * 0.85 / (double)perThread));
+        threads = std::min<long long>(threads, (long long)prop.multiProcessorCount * 2048);
+        if (threads < 1) { sim->err = "not enough device memory for one U0 live list"; return RA_E_NOMEM; }
+        d.grid = (int)((threads + 31) / 32);
+        d.smem = 0;
+        cudaError_t e = cudaMalloc(&d.dWorkspace, perThread * (size_t)d.grid * 32);
+        if (e != cudaSuccess) { sim->err = std::string("U0 workspace cudaMalloc failed: ") + cudaGetErrorString(e); return RA_E_NOMEM; }
+        return RA_OK;
+    }
     /* grid and per-block workspace */
     const bool isN = sim->variant == RA_VARIANT_N;
     const bool dump = sim->opt.dumpUEs != 0;
@@ -497,6 +538,7 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry ? 1 : 0; pt.R = ra_host_ring(&p);
         pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.arrCum = nullptr;
         ra_host_fill_point(&pt);
+        if (p.variant == RA_VARIANT_U0) ra_host_point_u0(&p, &pt);
         sim->hostPoints.push_back(pt);
         sim->arrCum.emplace_back(pt.nOcc);
         ra_host_arrcum(&p, sim->arrCum.back().data(), pt.nOcc);
@@ -556,7 +598,11 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
         a.worksN = d.dWorksN; a.cellRadius = sim->points[0].cellRadius;
         a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
-        if (sim->variant == RA_VARIANT_N) {
+        a.liveBase = (RuUE*)d.dWorkspace;
+        if (sim->variant == RA_VARIANT_U0) {
+            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, 32, 0, d.stream>>>(a, sim->cap);
+            else ra_u0_kernel<false><<<d.grid, 32, 0, d.stream>>>(a, sim->cap);
+        } else if (sim->variant == RA_VARIANT_N) {
             if (sim->opt.dumpUEs) ra_step_kernel_n<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
             else ra_step_kernel_n<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
         } else if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);

@@ -40,6 +40,9 @@ extern "C" int ra_params_default(ra_params* p, int variant) {
     p->hUT = 1.8;                   /* W:82 */
     p->geometry = 1;
     p->seed = 0;
+    if (variant == RA_VARIANT_U0) {    /* RandomAccessSimulator.c:48-59 */
+        p->nPreamble = 64; p->distribution = 1; p->geometry = 0;
+    }
     if (variant == RA_VARIANT_N) {     /* NOMA.c:41-57 */
         p->nGrantUL = 2; p->maxRarWindow = 5; p->maxMsg2TxCount = 10; p->cellRadius = 500;
     }
@@ -88,8 +91,13 @@ static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
 #define RA_BAD(...) do { snprintf(err, errLen, __VA_ARGS__); return RA_E_INVAL; } while (0)
-    if (p->variant != RA_VARIANT_W && p->variant != RA_VARIANT_N)
-        RA_BAD("variant %d is not built (RA_VARIANT_W = W/B dynamics, RA_VARIANT_N = NOMA.c)", p->variant);
+    if (p->variant != RA_VARIANT_W && p->variant != RA_VARIANT_N && p->variant != RA_VARIANT_U0)
+        RA_BAD("unknown variant %d (RA_VARIANT_W = 0, RA_VARIANT_U0 = 1, RA_VARIANT_N = 2)", p->variant);
+    if (p->variant == RA_VARIANT_U0) {
+        /* RandomAccessSimulator.c: Uniform traffic over 60 s with subframe 5 only (U0:57-60,77) */
+        if (p->distribution != 1) RA_BAD("variant U0 has Uniform traffic only (RandomAccessSimulator.c:57-60)");
+        if (p->accessTime != 5) RA_BAD("variant U0 has accessTime 5 hard-coded (RandomAccessSimulator.c:59)");
+    }
     if (p->variant == RA_VARIANT_N) {
         /* NOMA.c: Beta traffic only (N:675), rarWindow = 5 >= maxRarWindow is the only path that retransmits (N:453-455) */
         if (p->distribution == 1) RA_BAD("variant N has Beta traffic only (NOMA.c:675)");
@@ -137,6 +145,18 @@ void ra_host_fill_point(RaPointDev* pt) {
     int sh = 0;
     while (((pt->nUE - 1) >> sh) >= RA_HBINS) ++sh;
     pt->hshift = sh;
+}
+
+/* variant U0: RaPointDev.G carries nAccessUE = ceil(n*5/60000), at least 1 (U0:60-64) */
+void ra_host_point_u0(const ra_params* p, RaPointDev* pt) {
+    memset(pt, 0, sizeof *pt);
+    pt->nUE = p->nUE; pt->P = p->nPreamble; pt->BI = p->backoffIndicator; pt->A = 5;
+    pt->maxTime = ra_horizon_ms(p); pt->R = 1; pt->seed = p->seed;
+    const int maxTime = 60000, accessTime = 5;
+    int nAccessUE = ceil((float)p->nUE * (float)accessTime * 1.0 / (float)maxTime);
+    if (nAccessUE == 0) nAccessUE = 1;
+    pt->G = nAccessUE;
+    ra_host_fill_point(pt);
 }
 
 extern "C" const char* ra_version(void) { return "rach_b200 0.1 (sm_100a, variant W/B)"; }

@@ -9,6 +9,7 @@ int ra_host_ring(const ra_params* p);                          /* R: power of tw
 int ra_host_arrcum(const ra_params* p, int* arrCum, int nOcc); /* returns the final activeCheck */
 
 struct RaPointDev;
-void ra_host_fill_point(RaPointDev* pt);                        /* derived fields: magic numbers, hshift */
+void ra_host_fill_point(RaPointDev* pt);
+void ra_host_point_u0(const ra_params* p, RaPointDev* pt);      /* variant U0 point (G carries nAccessUE) */                        /* derived fields: magic numbers, hshift */
 
 #endif

@@ -38,7 +38,11 @@ extern "C" {
 #endif
 
 #define RA_VARIANT_W  0   /* RandomAccessWithNOMA.c / RandomAccessSimulatorBeta.c dynamics */
-#define RA_VARIANT_U0 1   /* RandomAccessSimulator.c legacy dynamics   (not built yet)     */
+#define RA_VARIANT_U0 1   /* RandomAccessSimulator.c legacy dynamics (U0:75-126, 157-266): Uniform 60 s,
+                             subframe 5, 64 preambles by default, no grant limit, hard drop after 10
+                             backoffs; ra_sim_dump_ues rows: timer active txTime preamble preambleChange
+                             rarWindow maxRarCounter preambleTxCounter msg2Flag connectionRequest msg4Flag
+                             raFailed nowBackoff 0 0 0 */
 #define RA_VARIANT_N  2   /* NOMA.c sector / gain-pairing dynamics (N:131-324, 449-566, 665-711):
                              nGrantUL = grants per sector (N:43), maxRarWindow <= 5 (N:45),
                              maxMsg2TxCount carries maxMsg1ReTx (N:46), cellRadius (N:56), Beta only */

@@ -182,3 +182,29 @@ extern "C" int emu_run_n(const ref_config* cfg, ref_result* res, int* perUE, flo
     return perUE ? emu_run_n_t<true>(cfg, res, perUE, (double*)geom, emu_threads)
                  : emu_run_n_t<false>(cfg, res, NULL, NULL, emu_threads);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Variant U0: rach_core_u0.cuh runs one replication per thread; here: called once.
+ * ------------------------------------------------------------------------------------------ */
+#include "rach_core_u0.cuh"
+
+extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, float* geom) {
+    (void)geom;
+    ra_params p; ra_params_default(&p, RA_VARIANT_U0);
+    p.nUE = cfg->nUE; p.nPreamble = cfg->nPreamble; p.backoffIndicator = cfg->backoffIndicator; p.seed = cfg->seed;
+    p.maxTimeMs = cfg->stopMs > 0 ? cfg->stopMs : 0;
+    char err[256];
+    if (ra_host_validate(&p, err, sizeof err) != RA_OK) { fprintf(stderr, "emu: %s\n", err); return -1; }
+    RaPointDev pt; memset(&pt, 0, sizeof pt);
+    ra_host_point_u0(&p, &pt);
+    std::vector<RuUE> live((size_t)pt.nUE);
+    RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = perUE;
+    RuStats st;
+    if (perUE) ru_run_replication<true>(job, live.data(), pt.nUE, &st);
+    else ru_run_replication<false>(job, live.data(), pt.nUE, &st);
+    memset(res, 0, sizeof *res);
+    res->simTimeMs = st.simTime; res->nSuccess = st.nSuccess; res->preambleTxSum = st.txSum; res->delaySum = st.delaySum;
+    res->collisionPreambles = st.collisionPreambles; res->totalPreambleTxop = st.totalPreambleTxop;
+    res->continueFailed = st.dropped; res->captured = 1;
+    return st.overflow ? -3 : 0;
+}

@@ -58,6 +58,13 @@ N_CASES = [
     ("n_retx3_r100_6000", dict(nUE=6000, maxMsg2TxCount=3, cellRadius=100.0, seed=5)),
 ]
 
+U0_CASES = [
+    ("u0_default_3000", dict(nUE=3000)),
+    ("u0_default_30000", dict(nUE=30000, seed=1)),                   # RandomAccessSimulator.c as shipped (64 preambles)
+    ("u0_p1_overload_40000", dict(nUE=40000, nPreamble=1, seed=2)),   # collisions, drops, phantom colliders
+    ("u0_p1_bi40_3000", dict(nUE=3000, nPreamble=1, backoffIndicator=40, seed=3)),
+]
+
 STAT_KEYS = ["simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "failCountSum",
              "continueFailed", "collisionPreambles", "totalPreambleTxop", "collisionScans",
              "totalScans", "draws", "maxDrawsPerUeMs", "nAccessUE", "averageDelay",
@@ -92,6 +99,18 @@ def main():
         if cfg.nUE <= 3000:
             ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
         print("%-28s %s" % (name, stats[name]["stats"]))
+    for name, kw in U0_CASES:
+        cfg = O.make_config_u0(**kw)
+        res, ue = O.run_ref_u0(cfg)
+        full = dict(O.DEFAULTS); full.update(O.U0_DEFAULTS); full.update(kw)
+        stats[name] = {"variant": "u0", "config": full,
+                       "stats": {k: getattr(res, k) for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum",
+                                                              "collisionPreambles", "totalPreambleTxop", "draws")},
+                       "ue_sha256": hashlib.sha256(np.ascontiguousarray(ue).tobytes()).hexdigest(),
+                       "dropped": int((ue[:, 11] == -1).sum())}
+        if cfg.nUE <= 3000:
+            ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
+        print("%-28s %s dropped %d" % (name, stats[name]["stats"], stats[name]["dropped"]))
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "golden_stats.json"), "w") as f:
         json.dump(stats, f, indent=1, sort_keys=True)

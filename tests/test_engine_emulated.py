@@ -95,3 +95,22 @@ def test_noma_variant_emulated(oracle, emu):
         np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
         zomb += int(((ue[:, 1] == 1) & (ue[:, 14] > 0) & (ue[:, 15] == 0) & (ue[:, 2] < p.simTimeMs - 100)).sum())
     assert zomb > 0      # restarts that can never transmit again (NOMA.c:538 + :692) were exercised
+
+
+def test_legacy_variant_emulated(oracle, emu):
+    """Variant U0 (rach_core_u0.cuh, one thread per replication) on the host against the U0 oracle."""
+    so = os.path.join(ROOT, "tests", "emu", "_build", "librach_emu.so")
+    f = oracle._lib(so, "emu_run_u0")
+    rnd = random.Random(8)
+    cases = [dict(nUE=2000), dict(nUE=20000, seed=2), dict(nUE=40000, nPreamble=1, seed=3)]
+    for _ in range(25):
+        cases.append(dict(nUE=rnd.choice([1, 2, 50, 400, 3000, 9000, 40000]), nPreamble=rnd.choice([1, 2, 3, 8, 64]),
+                          backoffIndicator=rnd.choice([1, 2, 5, 20, 40]), seed=rnd.getrandbits(60), rep=rnd.randrange(1000),
+                          stopMs=rnd.choice([0, 0, 3000, 20000])))
+    for kw in cases:
+        cfg = oracle.make_config_u0(**kw)
+        p, ue = oracle.run_port_u0(cfg)
+        e, ue2, _ = oracle._run(f, cfg, True, False)
+        for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop"):
+            assert getattr(p, k) == getattr(e, k), (k, kw)
+        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))

@@ -83,3 +83,25 @@ def test_noma_variant_against_noma_c(oracle):
             assert getattr(r, k) == getattr(p, k), (k, kw)
         np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
         np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
+
+
+def test_legacy_variant_against_randomaccesssimulator_c(oracle):
+    """rach_oracle_u0.c against RandomAccessSimulator.c itself in tape mode (with the two-line fix):
+    light load as shipped, and overload with few preambles where dropped UEs keep colliding (U0:207)."""
+    if not os.path.exists(os.path.join(os.path.dirname(oracle.__file__), "_ref", "libref_u0.so")):
+        pytest.skip("oracle/_ref/libref_u0.so not built")
+    rnd = random.Random(5)
+    cases = [dict(nUE=2000), dict(nUE=15000, seed=2), dict(nUE=40000, nPreamble=1, seed=3), dict(nUE=36000, nPreamble=2, backoffIndicator=5, seed=4)]
+    for _ in range(10):
+        cases.append(dict(nUE=rnd.choice([1, 2, 50, 400, 3000, 8000]), nPreamble=rnd.choice([1, 2, 3, 8, 64]),
+                          backoffIndicator=rnd.choice([1, 2, 5, 20, 40]), seed=rnd.getrandbits(60), rep=rnd.randrange(1000)))
+    dropped = 0
+    for kw in cases:
+        cfg = oracle.make_config_u0(**kw)
+        r, ue = oracle.run_ref_u0(cfg)
+        p, ue2 = oracle.run_port_u0(cfg)
+        for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop", "draws"):
+            assert getattr(r, k) == getattr(p, k), (k, kw)
+        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+        dropped += int((ue[:, 11] == -1).sum())
+    assert dropped > 0
