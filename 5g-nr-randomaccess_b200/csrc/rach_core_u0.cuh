@@ -33,11 +33,17 @@ RA_HD void ru_dump_row(int* o, const RuUE& u) {
     o[13] = 0; o[14] = 0; o[15] = 0;
 }
 
+
+/* Dropped UEs ("phantoms", raFailed == -1) are never processed again (U0:99) but still match the scan
+ * predicate of U0:207 in the one ms where txTime+2 == time; a group update then moves them to time+3
+ * (U0:228-229) so they can match again 5 ms later.  They are kept out of the live list in `ph[]`,
+ * chained per ms of their next possible match (pad0 = next node, -1 ends the chain). */
 template <bool DUMP>
-RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* out) {
+RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHead, int cap, RuStats* out) {
     const RaPointDev& pt = *job.pt;
     const int nUE = pt.nUE, P = pt.P, BI = pt.BI, maxTime = pt.maxTime, accessTime = 5;   /* U0:57,59 */
     const int nAccessUE = pt.G;                       /* host: ceil(n*5/60000), at least 1 (U0:60-64) */
+    const int ringMask = pt.R - 1;
     RuStats st; st.simTime = maxTime; st.nSuccess = 0; st.txSum = st.delaySum = 0;
     st.collisionPreambles = st.totalPreambleTxop = st.dropped = 0; st.overflow = 0;
     if (DUMP) for (int i = 0; i < nUE; ++i) {         /* calloc + initialUE, U0:46,149-155 */
@@ -45,7 +51,8 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* ou
         for (int k = 0; k < RA_DUMP_W; ++k) o[k] = 0;
         o[0] = -1; o[1] = -1; o[2] = -1; o[3] = -1;
     }
-    int nLive = 0, nDead = 0, activeCheck = 0, arrived = 0, time;
+    for (int i = 0; i <= ringMask; ++i) phHead[i] = -1;
+    int nLive = 0, nGone = 0, nPh = 0, activeCheck = 0, arrived = 0, time;
     for (time = 0; time < maxTime; time++) {
         if (time % accessTime == 1) {                 /* U0:77-94 (bound fixed: i < nUE) */
             if (activeCheck >= nUE) activeCheck = nUE; else activeCheck += nAccessUE;
@@ -59,9 +66,10 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* ou
                 live[nLive++] = u;
             }
         }
+        const int slot = time & ringMask;
         for (int a = 0; a < nLive; ++a) {
             RuUE u = live[a];
-            if (!(u.msg4Flag == 0 && u.raFailed != -1)) continue;            /* U0:99 */
+            if (u.pad1) continue;                                             /* finished or moved to ph[] */
             unsigned k = 0;
             if (u.active == 1 && u.msg2Flag == 0) {                           /* selectPreamble U0:157-197 */
                 if (u.preamble == -1) {
@@ -84,16 +92,29 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* ou
             if (u.txTime + 2 == time && u.txTime != -1) {                     /* preambleCollision U0:107-110, 200-233 */
                 int check = 0;
                 for (int b = 0; b < nLive; ++b)
-                    if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
+                    if (!live[b].pad1 && live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
+                for (int n = phHead[slot]; n >= 0; n = ph[n].pad0)
+                    if (ph[n].txTime + 2 == time && ph[n].preamble == u.preamble) check++;
                 if (check == 1) {
                     st.totalPreambleTxop++;
                     u.preambleTxCounter++; u.active = 2; u.txTime = time + 2; u.connectionRequest = 0; u.msg2Flag = 1;
                 } else {
                     st.collisionPreambles += check;
                     for (int b = 0; b < nLive; ++b)
-                        if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
+                        if (!live[b].pad1 && live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
                             live[b].rarWindow = 5; live[b].txTime = time + 3;
                         }
+                    /* phantoms of this class: same update, then they can match again at time+5 */
+                    int prev = -1;
+                    for (int n = phHead[slot]; n >= 0;) {
+                        const int next = ph[n].pad0;
+                        if (ph[n].txTime + 2 == time && ph[n].preamble == u.preamble) {
+                            ph[n].rarWindow = 5; ph[n].txTime = time + 3;
+                            if (prev < 0) phHead[slot] = next; else ph[prev].pad0 = next;
+                            ph[n].pad0 = phHead[(time + 5) & ringMask]; phHead[(time + 5) & ringMask] = n;
+                        } else prev = n;
+                        n = next;
+                    }
                     u = live[a];                                              /* the scanner may be a member */
                 }
             }
@@ -114,21 +135,32 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, int cap, RuStats* ou
                 u.timer++;
                 if (u.nowBackoff != 0) u.nowBackoff--;
             }
-            live[a] = u;
             if (u.msg4Flag == 1) {
-                st.txSum += u.preambleTxCounter; st.delaySum += u.timer; nDead++;
+                st.txSum += u.preambleTxCounter; st.delaySum += u.timer; nGone++; u.pad1 = 1;
                 if (DUMP) ru_dump_row(job.dump + (size_t)u.idx * RA_DUMP_W, u);
+            } else if (u.raFailed == -1) {                                    /* frozen from now on: to the phantom calendar */
+                if (nPh >= cap) { st.overflow = 1; }
+                else {
+                    RuUE n = u; const int s2 = (u.txTime + 2) & ringMask;
+                    n.pad0 = phHead[s2]; n.pad1 = 0; ph[nPh] = n; phHead[s2] = nPh; nPh++;
+                }
+                nGone++; u.pad1 = 1;
             }
+            live[a] = u;
         }
+        phHead[slot] = -1;                                                    /* whoever was not hit never matches again */
         if (st.nSuccess == nUE) break;                                        /* U0:122-125 */
-        if (nDead > 16 && nDead * 4 > nLive) {                                /* drop the finished ones, keep index order */
+        if (nGone > 16 && nGone * 4 > nLive) {                                /* compact, keeping index order */
             int w = 0;
-            for (int a = 0; a < nLive; ++a) if (live[a].msg4Flag == 0) { if (w != a) live[w] = live[a]; ++w; }
-            nLive = w; nDead = 0;
+            for (int a = 0; a < nLive; ++a) if (!live[a].pad1) { if (w != a) live[w] = live[a]; ++w; }
+            nLive = w; nGone = 0;
         }
     }
     st.simTime = time;
-    if (DUMP) for (int a = 0; a < nLive; ++a) if (live[a].msg4Flag == 0) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
+    if (DUMP) {
+        for (int a = 0; a < nLive; ++a) if (!live[a].pad1) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
+        for (int n = 0; n < nPh; ++n) ru_dump_row(job.dump + (size_t)ph[n].idx * RA_DUMP_W, ph[n]);
+    }
     *out = st;
 }
 

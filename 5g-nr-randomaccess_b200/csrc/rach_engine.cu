@@ -285,7 +285,11 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel_n(RaKernelArgs 
 template <bool DUMP>
 __global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    RuUE* live = a.liveBase + (size_t)gtid * (size_t)cap;
+    /* per thread: live list [cap], phantom store [cap], phantom calendar heads [maxR ints] */
+    const size_t perThread = 2 * (size_t)cap + ((size_t)a.maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE);
+    RuUE* live = a.liveBase + (size_t)gtid * perThread;
+    RuUE* ph = live + cap;
+    int* phHead = reinterpret_cast<int*>(ph + cap);
     for (;;) {
         const int jobId = (int)atomicAdd(a.jobCounter, 1u);
         if (jobId >= a.nJobs) break;
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap) {
         RaJob job; job.pt = pt; job.rep = a.jobRep[jobId];
         job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
         RuStats st;
-        ru_run_replication<DUMP>(job, live, cap, &st);
+        ru_run_replication<DUMP>(job, live, ph, phHead, cap, &st);
         ra_stats o; memset(&o, 0, sizeof o);
         o.simTimeMs = st.simTime; o.nSuccess = st.nSuccess; o.preambleTxSum = st.txSum; o.delaySum = st.delaySum;
         o.continueFailed = st.dropped; o.finalSuccess = st.nSuccess;
@@ -428,7 +432,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
         /* one thread per replication, 32 threads per block; live list of cap UEs (64 B each) per thread */
         size_t freeB = 0, totalB = 0;
         RA_CUDA(sim, cudaMemGetInfo(&freeB, &totalB));
-        const size_t perThread = sizeof(RuUE) * (size_t)sim->cap;
+        const size_t perThread = sizeof(RuUE) * (2 * (size_t)sim->cap + ((size_t)sim->maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE));
         long long threads = std::min<long long>(nJobs, (long long)((double)freeB * 0.85 / (double)perThread));
         threads = std::min<long long>(threads, (long long)prop.multiProcessorCount * 2048);
         if (threads < 1) { sim->err = "not enough device memory for one U0 live list"; return RA_E_NOMEM; }

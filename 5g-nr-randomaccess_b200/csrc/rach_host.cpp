@@ -151,7 +151,8 @@ void ra_host_fill_point(RaPointDev* pt) {
 void ra_host_point_u0(const ra_params* p, RaPointDev* pt) {
     memset(pt, 0, sizeof *pt);
     pt->nUE = p->nUE; pt->P = p->nPreamble; pt->BI = p->backoffIndicator; pt->A = 5;
-    pt->maxTime = ra_horizon_ms(p); pt->R = 1; pt->seed = p->seed;
+    pt->maxTime = ra_horizon_ms(p); pt->seed = p->seed;
+    pt->R = next_pow2(p->backoffIndicator + 9);          /* phantom calendar: next match <= time + BI + 3 */
     const int maxTime = 60000, accessTime = 5;
     int nAccessUE = ceil((float)p->nUE * (float)accessTime * 1.0 / (float)maxTime);
     if (nAccessUE == 0) nAccessUE = 1;

@@ -197,11 +197,12 @@ extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, fl
     if (ra_host_validate(&p, err, sizeof err) != RA_OK) { fprintf(stderr, "emu: %s\n", err); return -1; }
     RaPointDev pt; memset(&pt, 0, sizeof pt);
     ra_host_point_u0(&p, &pt);
-    std::vector<RuUE> live((size_t)pt.nUE);
+    std::vector<RuUE> live((size_t)pt.nUE), ph((size_t)pt.nUE);
+    std::vector<int> phHead((size_t)pt.R);
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = perUE;
     RuStats st;
-    if (perUE) ru_run_replication<true>(job, live.data(), pt.nUE, &st);
-    else ru_run_replication<false>(job, live.data(), pt.nUE, &st);
+    if (perUE) ru_run_replication<true>(job, live.data(), ph.data(), phHead.data(), pt.nUE, &st);
+    else ru_run_replication<false>(job, live.data(), ph.data(), phHead.data(), pt.nUE, &st);
     memset(res, 0, sizeof *res);
     res->simTimeMs = st.simTime; res->nSuccess = st.nSuccess; res->preambleTxSum = st.txSum; res->delaySum = st.delaySum;
     res->collisionPreambles = st.collisionPreambles; res->totalPreambleTxop = st.totalPreambleTxop;
