@@ -58,6 +58,7 @@ int oracle_run_u0(const ref_config* cfg, ref_result* res, int* perUE, float* geo
     int nAccessUE = ceil((float)nUE * (float)accessTime * 1.0 / (float)maxTime);   /* U0:60 */
     if (nAccessUE == 0) nAccessUE = 1;
     int activeCheck = 0, nSuccess = 0, time;
+    int lo = 0, hi = 0;   /* UEs below lo have all finished, UEs from hi on have not arrived: both inert */
     long long collisionPreambles = 0, totalPreambleTxop = 0;
 
     for (time = 0; time < maxTime; time++) {
@@ -69,17 +70,19 @@ int oracle_run_u0(const ref_config* cfg, ref_result* res, int* perUE, float* geo
                 uue* u = c.ue + i;
                 if (u->active == -1) { u->active = 1; u->txTime = time + 1; u->timer = 0; u->msg2Flag = 0; }
             }
+            hi = activeCheck + 1 < nUE ? activeCheck + 1 : nUE;
         }
+        while (lo < hi && c.ue[lo].msg4Flag == 1) lo++;
         memset(cnt, 0, sizeof(int) * (size_t)P);
         int nPh = 0;
-        for (int i = 0; i < nUE; ++i) {
+        for (int i = lo; i < hi; ++i) {
             uue* u = c.ue + i;
             if (u->active == 1 && u->txTime + 2 == time && u->preamble >= 0) {
                 cnt[u->preamble]++;
                 if (u->raFailed == -1) phantom[nPh++] = i;
             }
         }
-        for (int i = 0; i < nUE; ++i) {
+        for (int i = lo; i < hi; ++i) {
             uue* u = c.ue + i;
             if (!(u->msg4Flag == 0 && u->raFailed != -1)) continue;       /* U0:99 */
             /* group update by a lower-index scanner of my preamble, U0:228-229 */

@@ -257,7 +257,7 @@ def test_legacy_u0_fixtures_and_fuzz(pkg, golden, oracle):
     rep = cases[0][2]
     assert all(c[2] == rep for c in cases)
     for _ in range(12):
-        cases.append((None, dict(nUE=rnd.choice([1, 2, 50, 400, 3000, 9000, 40000]), nPreamble=rnd.choice([1, 2, 3, 8, 64]),
+        cases.append((None, dict(nUE=rnd.choice([1, 2, 50, 400, 3000, 9000, 24001]), nPreamble=rnd.choice([1, 2, 3, 8, 64]),
                                  backoffIndicator=rnd.choice([1, 2, 5, 20, 40]), seed=rnd.getrandbits(60)), rep, None))
     pts = [pkg.default_params(variant=1, **kw) for _, kw, _, _ in cases]
     with pkg.RachSim(pts, reps=1, devices=[0], rep_offset=rep, dump_ues=True) as sim:
