@@ -17,9 +17,16 @@
 
 #include "rach_core.cuh"
 
-struct RuUE {            /* 64 bytes */
-    int idx, timer, active, txTime, preamble, rarWindow, maxRarCounter, preambleTxCounter;
-    int msg2Flag, connectionRequest, msg4Flag, preambleChange, raFailed, nowBackoff, pad0, pad1;
+#ifdef __CUDACC__
+#define RU_ALIGN __align__(16)
+#else
+#define RU_ALIGN alignas(16)
+#endif
+struct RU_ALIGN RuUE {   /* 64 bytes; the first 16 are all a collision scan reads (U0:207-209) */
+    int idx, active, txTime, preamble;      /* live-list copy: active == -2 = gone (finished / moved to ph[]) */
+    int timer, rarWindow, maxRarCounter, preambleTxCounter;
+    int msg2Flag, connectionRequest, msg4Flag, preambleChange;
+    int raFailed, nowBackoff, pad0, pad1;   /* pad0: next node of a phantom chain */
 };
 
 struct RuStats { int simTime, nSuccess; long long txSum, delaySum, collisionPreambles, totalPreambleTxop, dropped; int overflow; };
@@ -69,7 +76,7 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
         const int slot = time & ringMask;
         for (int a = 0; a < nLive; ++a) {
             RuUE u = live[a];
-            if (u.pad1) continue;                                             /* finished or moved to ph[] */
+            if (u.active == -2) continue;                                     /* finished or moved to ph[] */
             unsigned k = 0;
             if (u.active == 1 && u.msg2Flag == 0) {                           /* selectPreamble U0:157-197 */
                 if (u.preamble == -1) {
@@ -88,11 +95,11 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                     }
                 }
             }
-            live[a] = u;                                                      /* the scan below reads the list */
-            if (u.txTime + 2 == time && u.txTime != -1) {                     /* preambleCollision U0:107-110, 200-233 */
+            if (u.txTime + 2 == time && u.txTime != -1) {
+                live[a] = u;                                                  /* the scan below reads the list */                     /* preambleCollision U0:107-110, 200-233 */
                 int check = 0;
                 for (int b = 0; b < nLive; ++b)
-                    if (!live[b].pad1 && live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
+                    if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
                 for (int n = phHead[slot]; n >= 0; n = ph[n].pad0)
                     if (ph[n].txTime + 2 == time && ph[n].preamble == u.preamble) check++;
                 if (check == 1) {
@@ -101,7 +108,7 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 } else {
                     st.collisionPreambles += check;
                     for (int b = 0; b < nLive; ++b)
-                        if (!live[b].pad1 && live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
+                        if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
                             live[b].rarWindow = 5; live[b].txTime = time + 3;
                         }
                     /* phantoms of this class: same update, then they can match again at time+5 */
@@ -136,15 +143,16 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 if (u.nowBackoff != 0) u.nowBackoff--;
             }
             if (u.msg4Flag == 1) {
-                st.txSum += u.preambleTxCounter; st.delaySum += u.timer; nGone++; u.pad1 = 1;
+                st.txSum += u.preambleTxCounter; st.delaySum += u.timer; nGone++;
                 if (DUMP) ru_dump_row(job.dump + (size_t)u.idx * RA_DUMP_W, u);
+                u.active = -2;
             } else if (u.raFailed == -1) {                                    /* frozen from now on: to the phantom calendar */
                 if (nPh >= cap) { st.overflow = 1; }
                 else {
                     RuUE n = u; const int s2 = (u.txTime + 2) & ringMask;
-                    n.pad0 = phHead[s2]; n.pad1 = 0; ph[nPh] = n; phHead[s2] = nPh; nPh++;
+                    n.pad0 = phHead[s2]; ph[nPh] = n; phHead[s2] = nPh; nPh++;
                 }
-                nGone++; u.pad1 = 1;
+                nGone++; u.active = -2;
             }
             live[a] = u;
         }
@@ -152,13 +160,13 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
         if (st.nSuccess == nUE) break;                                        /* U0:122-125 */
         if (nGone > 16 && nGone * 4 > nLive) {                                /* compact, keeping index order */
             int w = 0;
-            for (int a = 0; a < nLive; ++a) if (!live[a].pad1) { if (w != a) live[w] = live[a]; ++w; }
+            for (int a = 0; a < nLive; ++a) if (live[a].active != -2) { if (w != a) live[w] = live[a]; ++w; }
             nLive = w; nGone = 0;
         }
     }
     st.simTime = time;
     if (DUMP) {
-        for (int a = 0; a < nLive; ++a) if (!live[a].pad1) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
+        for (int a = 0; a < nLive; ++a) if (live[a].active != -2) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
         for (int n = 0; n < nPh; ++n) ru_dump_row(job.dump + (size_t)ph[n].idx * RA_DUMP_W, ph[n]);
     }
     *out = st;

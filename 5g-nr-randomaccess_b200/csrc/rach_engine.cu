@@ -34,6 +34,7 @@
 #define RA_MINB (1024 / RA_NT) /* resident blocks per SM the register budget is sized for */
 #endif
 #define RA_NPHASE 10
+#define RA_U0_NT 8           /* variant U0: threads (= replications) per block; few, so the live lists stay in L1 */
 #define RA_TICK(k) do { if (tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
 struct RaKernelArgs {
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel_n(RaKernelArgs 
  * Variant U0 (RandomAccessSimulator.c): one THREAD per replication (rach_core_u0.cuh).
  * ------------------------------------------------------------------------------------------ */
 template <bool DUMP>
-__global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap) {
+__global__ void __launch_bounds__(RA_U0_NT) ra_u0_kernel(RaKernelArgs a, int cap) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     /* per thread: live list [cap], phantom store [cap], phantom calendar heads [maxR ints] */
     const size_t perThread = 2 * (size_t)cap + ((size_t)a.maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE);
@@ -436,9 +437,9 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
         long long threads = std::min<long long>(nJobs, (long long)((double)freeB * 0.85 / (double)perThread));
         threads = std::min<long long>(threads, (long long)prop.multiProcessorCount * 2048);
         if (threads < 1) { sim->err = "not enough device memory for one U0 live list"; return RA_E_NOMEM; }
-        d.grid = (int)((threads + 31) / 32);
+        d.grid = (int)((threads + RA_U0_NT - 1) / RA_U0_NT);
         d.smem = 0;
-        cudaError_t e = cudaMalloc(&d.dWorkspace, perThread * (size_t)d.grid * 32);
+        cudaError_t e = cudaMalloc(&d.dWorkspace, perThread * (size_t)d.grid * RA_U0_NT);
         if (e != cudaSuccess) { sim->err = std::string("U0 workspace cudaMalloc failed: ") + cudaGetErrorString(e); return RA_E_NOMEM; }
         return RA_OK;
     }
@@ -604,8 +605,8 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
         a.liveBase = (RuUE*)d.dWorkspace;
         if (sim->variant == RA_VARIANT_U0) {
-            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, 32, 0, d.stream>>>(a, sim->cap);
-            else ra_u0_kernel<false><<<d.grid, 32, 0, d.stream>>>(a, sim->cap);
+            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, RA_U0_NT, 0, d.stream>>>(a, sim->cap);
+            else ra_u0_kernel<false><<<d.grid, RA_U0_NT, 0, d.stream>>>(a, sim->cap);
         } else if (sim->variant == RA_VARIANT_N) {
             if (sim->opt.dumpUEs) ra_step_kernel_n<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
             else ra_step_kernel_n<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);

@@ -6,7 +6,8 @@ pkg = importlib.import_module("5g-nr-randomaccess_b200")
 out = {}
 for name, p, reps in (("uniform_100k_x256", pkg.default_params(nUE=100000, distribution=1), 256),
                       ("noma_N_50k_x1024", pkg.default_params(variant=2, nUE=50000), 1024),
-                      ("w_geometry_50k_x1024", pkg.default_params(nUE=50000, cellRadius=400.0), 1024)):
+                      ("w_geometry_50k_x1024", pkg.default_params(nUE=50000, cellRadius=400.0), 1024),
+                      ("legacy_U0_100k_x1024", pkg.default_params(variant=1, nUE=100000), 1024)):
     with pkg.RachSim([p], reps=reps, devices=[0]) as sim:
         sim.run(); sim.run()
         st = sim.stats_all()
