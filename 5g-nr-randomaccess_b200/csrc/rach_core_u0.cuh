@@ -95,8 +95,8 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                     }
                 }
             }
-            if (u.txTime + 2 == time && u.txTime != -1) {
-                live[a] = u;                                                  /* the scan below reads the list */                     /* preambleCollision U0:107-110, 200-233 */
+            if (u.txTime + 2 == time && u.txTime != -1) {                     /* preambleCollision U0:107-110, 200-233 */
+                live[a] = u;                                                  /* the scan below reads the list */
                 int check = 0;
                 for (int b = 0; b < nLive; ++b)
                     if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
