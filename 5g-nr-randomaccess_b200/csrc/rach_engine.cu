@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
             ra_carve(s, ra_dyn_smem, sPt.R, sPt.P);
         }
         __syncthreads();
-        const RaPointDev& pt = sPt;
+        const RaPointDev& pt = sPt;         /* (a thread-local copy was measured: spills, 3 % slower) */
         RaJob job; job.pt = &pt; job.rep = a.jobRep[jobId];
         job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
         ra_job_init<DUMP>(job, s, tid, nt);
@@ -109,18 +109,23 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
             __syncthreads();
             RA_TICK(0);
             {
-                /* movers: 128-bit coalesced loads of bucket T, next record in flight while this one is processed */
+                /* movers: 128-bit coalesced loads of bucket T; two records per thread and iteration so that
+                 * their two Philox chains interleave (the chain is 10 dependent rounds), next pair prefetched */
                 const unsigned nMov = s.nMov;
                 const uint4* bT = w.bucket + (size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap;
+                const uint4 dead = make_uint4(RA_DEAD, 0, 0, 0);
                 unsigned i = tid;
-                uint4 cur = make_uint4(RA_DEAD, 0, 0, 0);
-                if (i < nMov) cur = bT[i];
+                uint4 c0 = i < nMov ? bT[i] : dead;
+                uint4 c1 = i + nt < nMov ? bT[i + nt] : dead;
                 while (i < nMov) {
-                    const unsigned ni = i + nt;
-                    uint4 nxt = make_uint4(RA_DEAD, 0, 0, 0);
-                    if (ni < nMov) nxt = bT[ni];
-                    ra_phase1_mover<DUMP>(job, w, s, acc, T, i, cur);
-                    cur = nxt; i = ni;
+                    const unsigned ni = i + 2 * nt;
+                    const uint4 n0 = ni < nMov ? bT[ni] : dead;
+                    const uint4 n1 = ni + nt < nMov ? bT[ni + nt] : dead;
+                    const rach_u32x4 d0 = ra_draws(job, c0.x, T);
+                    const rach_u32x4 d1 = ra_draws(job, c1.x, T);
+                    ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i, c0, d0);
+                    ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + nt, c1, d1);
+                    c0 = n0; c1 = n1; i = ni;
                 }
                 const unsigned n1 = nMov + (unsigned)s.nArr + s.nM3;
                 for (i = nMov + tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
