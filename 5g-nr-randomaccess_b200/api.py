@@ -48,7 +48,7 @@ assert STATS_DTYPE.itemsize == C.sizeof(RaStats)
 
 class RaOptions(C.Structure):
     _fields_ = [("repOffset", C.c_int), ("dumpUEs", C.c_int), ("ctasPerSM", C.c_int),
-                ("reserved", C.c_int * 5)]
+                ("phaseTimers", C.c_int), ("reserved", C.c_int * 4)]
 
 
 SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_sim_run", "ra_sim_stats",
@@ -124,13 +124,14 @@ def arrival_schedule(params):
 class RachSim:
     """points x reps replications of the RACH state machine on the GPU(s)."""
 
-    def __init__(self, points, reps=1, devices=None, rep_offset=0, dump_ues=False, ctas_per_sm=0):
+    def __init__(self, points, reps=1, devices=None, rep_offset=0, dump_ues=False, ctas_per_sm=0, phase_timers=False):
         lib = load_lib()
         self._lib = lib
         self.points = list(points)
         self.reps = int(reps)
         arr = (RaParams * len(self.points))(*self.points)
-        opt = RaOptions(repOffset=rep_offset, dumpUEs=1 if dump_ues else 0, ctasPerSM=ctas_per_sm)
+        opt = RaOptions(repOffset=rep_offset, dumpUEs=1 if dump_ues else 0, ctasPerSM=ctas_per_sm,
+                        phaseTimers=1 if phase_timers else 0)
         if devices is None:
             dev, nd = None, 0
         else:

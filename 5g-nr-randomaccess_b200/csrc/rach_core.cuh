@@ -52,8 +52,16 @@ typedef unsigned long long ra_u64;
 #define RA_M3RING 64
 #define RA_DUMP_W 16
 #define RA_HBINS 1024       /* histogram bins of the grant selection            */
+#ifndef RA_SCAP
 #define RA_SCAP  2048       /* singleton scans of one ms kept in shared memory  */
+#endif
 #define RA_MAGIC5 858993460u /* ra_magic(5) */
+#ifndef RA_LCAP
+#define RA_LCAP  1024       /* re-transmitters of one ms kept in shared memory (rest: global) */
+#endif
+#ifndef RA_UCAP
+#define RA_UCAP  256        /* uncertain movers of one ms kept in shared memory (rest: global) */
+#endif
 
 /* ---- atomics: CUDA on the device, plain read-modify-write in the host emulator ---------- */
 #ifdef __CUDA_ARCH__
@@ -98,6 +106,9 @@ struct RaShared {
     unsigned *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each     */
     unsigned* hist;           /* [RA_HBINS] singleton scans per index bin (grant selection) */
     unsigned* sIdx;           /* [RA_SCAP]  first singleton indices of the ms                */
+    uint4*    sLand;          /* [RA_LCAP]  first re-transmitter records of the ms           */
+    unsigned* sLandMeta;      /* [RA_LCAP]                                                   */
+    uint4*    sUnc;           /* [RA_UCAP]  first uncertain movers of the ms                 */
     int grantCheck, activeCheck, acOld, nArr, overflow, pad0;
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant, nNl, pad1;
@@ -156,6 +167,15 @@ RA_HD unsigned ra_first_scan(const RaShared& s, unsigned p) {     /* s[p] of the
     return a < b ? a : b;
 }
 
+/* per-ms work lists: the first entries live in shared memory (the small phases then never wait for
+ * L2), the overflow in the block's global workspace */
+RA_HD uint4 ra_lrec_get(const RaWork& w, const RaShared& s, unsigned l) { return l < RA_LCAP ? s.sLand[l] : w.landerRec[l]; }
+RA_HD unsigned ra_lmeta_get(const RaWork& w, const RaShared& s, unsigned l) { return l < RA_LCAP ? s.sLandMeta[l] : w.landerMeta[l]; }
+RA_HD void ra_lmeta_set(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l < RA_LCAP) s.sLandMeta[l] = v; else w.landerMeta[l] = v; }
+RA_HD void ra_lmeta_add(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l < RA_LCAP) RA_AADD(&s.sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
+RA_HD void ra_unc_set(const RaWork& w, RaShared& s, unsigned u, const uint4& e) { if (u < RA_UCAP) s.sUnc[u] = e; else w.uncertain[u] = e; }
+RA_HD uint4 ra_unc_get(const RaWork& w, const RaShared& s, unsigned u) { return u < RA_UCAP ? s.sUnc[u] : w.uncertain[u]; }
+
 /* append a record to move bucket `m`; returns its position */
 RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
     unsigned slot = (unsigned)m & (unsigned)(pt.R - 1);
@@ -195,7 +215,8 @@ RA_HD void ra_msg3_push(const RaWork& w, RaShared& s, int due, const uint4& rec)
 RA_HD void ra_lander_push(const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
     unsigned l = RA_AADD(&s.nLanders, 1u);
     if (l >= (unsigned)w.cap) { s.overflow = 1; return; }
-    w.landerRec[l] = rec; w.landerMeta[l] = member;
+    if (l < RA_LCAP) { s.sLand[l] = rec; s.sLandMeta[l] = member; }
+    else { w.landerRec[l] = rec; w.landerMeta[l] = member; }
 }
 
 /* ---- dump helpers (DUMP builds only) ------------------------------------------------------ */
@@ -312,7 +333,7 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
     if (uncertain) {
         unsigned u = RA_AADD(&s.nUnc, 1u);
-        w.uncertain[u] = make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0);
+        ra_unc_set(w, s, u, make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0));
         if (limit) {
             if (X == T) { unsigned c = RA_AADD(&s.nC3, 1u); w.c3[c] = make_uint4(idx, p0, pnew, 0); }
             return;
@@ -419,7 +440,7 @@ RA_HD void ra_phase2_serial(const RaWork& w, RaShared& s) {
 template <bool DUMP>
 RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned u) {
     const RaPointDev& pt = *job.pt;
-    const uint4 e = w.uncertain[u];
+    const uint4 e = ra_unc_get(w, s, u);
     const unsigned idx = e.y, p0 = e.z & 0xFFu;
     const unsigned sp = ra_first_scan(s, p0);
     if (idx < sp) RA_AADD(&s.before[p0], 1u);              /* left the class before its first scan */
@@ -448,13 +469,13 @@ RA_HD void ra_phase3b_item(const RaWork& w, RaShared& s, unsigned e) {
     unsigned sq = ra_first_scan(s, q);
     if (sq != RA_INF32 && sq > k && sq == s.l1[q]) { bestIdx = sq; bestRef = 0x80000000u | q; }
     for (unsigned l = 0; l < s.nLanders; ++l) {
-        const uint4 lr = w.landerRec[l];
+        const uint4 lr = ra_lrec_get(w, s, l);
         if (ra_rec_p(lr) == q && lr.x > k && lr.x < bestIdx) { bestIdx = lr.x; bestRef = l; }
     }
     if (bestIdx == RA_INF32) return;
     w.e1Meta[e] = 1;
     if (bestRef & 0x80000000u) RA_AADD(&s.extraFirst[q], 1u);
-    else RA_AADD(&w.landerMeta[bestRef], 256u);
+    else ra_lmeta_add(w, s, bestRef, 256u);
 }
 
 /* =========================================================================================
@@ -490,8 +511,8 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
     }
     const unsigned l = item - (unsigned)pt.P;
     if (l >= s.nLanders) return;
-    const uint4 r = w.landerRec[l];
-    const unsigned q = ra_rec_p(r), meta = w.landerMeta[l];
+    const uint4 r = ra_lrec_get(w, s, l);
+    const unsigned q = ra_rec_p(r), meta = ra_lmeta_get(w, s, l);
     unsigned size;
     if (r.x == ra_first_scan(s, q)) size = s.N[q] - s.before[q] + ((meta & 1u) ? 0u : 1u) + (meta >> 8);
     else size = 1u + (meta >> 8);
@@ -499,7 +520,7 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
     if (size == 1) {
         ra_single_push(pt, w, s, r.x);
     } else {
-        w.landerMeta[l] = meta | 2u;                        /* collided */
+        ra_lmeta_set(w, s, l, meta | 2u);                   /* collided */
     }
 }
 
@@ -599,8 +620,8 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     }
     item -= (unsigned)pt.P;
     if (item < s.nLanders) {
-        uint4 r = w.landerRec[item];
-        const unsigned meta = w.landerMeta[item];
+        uint4 r = ra_lrec_get(w, s, item);
+        const unsigned meta = ra_lmeta_get(w, s, item);
         if (!(meta & 2u) && ra_granted(s, r.x)) {
             if (DUMP) { int* row = job.dump + (size_t)r.x * RA_DUMP_W; row[8] = 0; row[9] = (int)ra_rec_mrc(r); }
             r.y = (unsigned)(T + 11);

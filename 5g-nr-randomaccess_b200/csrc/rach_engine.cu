@@ -35,7 +35,7 @@
 #endif
 #define RA_NPHASE 10
 #define RA_U0_NT 8           /* variant U0: threads (= replications) per block; few, so the live lists stay in L1 */
-#define RA_TICK(k) do { if (tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
+#define RA_TICK(k) do { if (timers && tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
 struct RaKernelArgs {
     const RaPointDev* points;
@@ -57,6 +57,9 @@ struct RaKernelArgs {
 };
 
 __device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R, int P) {
+    s.sLand = reinterpret_cast<uint4*>(base);                  base += sizeof(uint4) * RA_LCAP;
+    s.sUnc = reinterpret_cast<uint4*>(base);                   base += sizeof(uint4) * RA_UCAP;
+    s.sLandMeta = reinterpret_cast<unsigned*>(base);           base += sizeof(unsigned) * RA_LCAP;
     s.minI = reinterpret_cast<unsigned*>(base);                base += sizeof(unsigned) * (size_t)R * P;
     s.cnt = reinterpret_cast<unsigned*>(base);                 base += sizeof(unsigned) * (size_t)R * P;
     s.bcount = reinterpret_cast<unsigned*>(base);              base += sizeof(unsigned) * (size_t)R;
@@ -68,7 +71,8 @@ __device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R
 }
 
 static size_t ra_smem_bytes(int R, int P) {
-    return sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
+    return sizeof(uint4) * (RA_LCAP + RA_UCAP) + sizeof(unsigned) * RA_LCAP +
+           sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
            sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P + sizeof(unsigned) * (RA_HBINS + RA_SCAP);
 }
 
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
     __shared__ int sJob;
     __shared__ ra_u64 sCyc[RA_NPHASE];
     long long tick = 0;
+    const bool timers = a.phaseCycles != nullptr;     /* profiling aid (ra_options.phaseTimers), off by default */
     if (threadIdx.x < RA_NPHASE) sCyc[threadIdx.x] = 0;
     const int tid = threadIdx.x, nt = blockDim.x;
     const RaWork w = a.works[blockIdx.x];
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
         __syncthreads();
 
         int simTime = pt.maxTime;
-        if (tid == 0) tick = clock64();
+        if (timers && tid == 0) tick = clock64();
         for (int T = 0;; ++T) {
             ra_phase0(job, s, T, tid, nt);
             __syncthreads();
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
         }
     }
     __syncthreads();
-    if (tid < RA_NPHASE && sCyc[tid]) atomicAdd(&a.phaseCycles[tid], sCyc[tid]);
+    if (timers && tid < RA_NPHASE && sCyc[tid]) atomicAdd(&a.phaseCycles[tid], sCyc[tid]);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -603,7 +608,7 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         RA_CUDA(sim, cudaMemsetAsync(d.dCyc, 0, sizeof(ra_u64) * RA_NPHASE, d.stream));
         RaKernelArgs a;
         a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
-        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = d.dCyc;
+        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = sim->opt.phaseTimers ? d.dCyc : nullptr;
         a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
         RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
         a.worksN = d.dWorksN; a.cellRadius = sim->points[0].cellRadius;

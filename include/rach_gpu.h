@@ -99,7 +99,8 @@ typedef struct ra_options {
     int repOffset;      /* tape replication id of local rep 0 (multi-process sharding)        */
     int dumpUEs;        /* 1 = keep the 16-int per-UE final record of every replication       */
     int ctasPerSM;      /* 0 = engine default; resident CTAs per SM of the step kernel        */
-    int reserved[5];
+    int phaseTimers;    /* 1 = collect per-phase cycle counters (ra_sim_phase_cycles); costs ~2 % */
+    int reserved[4];
 } ra_options;
 
 typedef struct ra_sim ra_sim;

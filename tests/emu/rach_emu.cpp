@@ -57,6 +57,8 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     s.cnt = cnt.data(); s.minI = minI.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
     s.N = cls.data(); s.l1 = s.N + pt.P; s.nlList = s.l1 + pt.P; s.l1m = s.nlList + pt.P; s.l2 = s.l1m + pt.P;
     s.hist = hist.data(); s.sIdx = sIdx.data();
+    std::vector<uint4> sLand(RA_LCAP), sUnc(RA_UCAP); std::vector<unsigned> sLandMeta(RA_LCAP);
+    s.sLand = sLand.data(); s.sUnc = sUnc.data(); s.sLandMeta = sLandMeta.data();
     s.before = s.l2 + pt.P; s.extraFirst = s.before + pt.P; s.clsSize = s.extraFirst + pt.P;
 
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;

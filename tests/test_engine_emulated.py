@@ -114,3 +114,28 @@ def test_legacy_variant_emulated(oracle, emu):
         for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop"):
             assert getattr(p, k) == getattr(e, k), (k, kw)
         np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+
+
+def test_work_list_overflow_paths(oracle, tmp_path):
+    """The per-ms work lists keep their first entries in shared memory and spill to global memory
+    (RA_LCAP / RA_UCAP / RA_SCAP in rach_core.cuh).  Built here with capacities of 3 / 2 / 2 so that
+    every run overflows them; results must not change."""
+    so = str(tmp_path / "librach_emu_small.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DRA_LCAP=3", "-DRA_UCAP=2", "-DRA_SCAP=2",
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"),
+                           "-I", os.path.join(ROOT, "5g-nr-randomaccess_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "emu", "rach_emu.cpp"),
+                           os.path.join(ROOT, "5g-nr-randomaccess_b200", "csrc", "rach_host.cpp"), "-o", so])
+    f = oracle._lib(so, "emu_run")
+    rnd = random.Random(5)
+    for _ in range(25):
+        kw = dict(nUE=rnd.choice([300, 1500, 4000, 9000]), nPreamble=rnd.choice([2, 3, 8, 54]),
+                  backoffIndicator=rnd.choice([1, 2, 5, 20]), nGrantUL=rnd.choice([1, 2, 4, 12]),
+                  maxRarWindow=rnd.choice([2, 3, 6]), maxMsg2TxCount=rnd.choice([0, 1, 3, 9]),
+                  accessTime=rnd.choice([1, 5, 5, 7]), seed=rnd.getrandbits(64), rep=rnd.randrange(5000))
+        cfg = oracle.make_config(**kw)
+        p, ue, _ = oracle.run_port(cfg)
+        e, ue2, _ = oracle._run(f, cfg, True, False)
+        for k in KEYS:
+            assert getattr(p, k) == getattr(e, k), (k, kw)
+        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))

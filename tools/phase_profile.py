@@ -4,10 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("5g-nr-randomaccess_b200")
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=592); ap.add_argument("--nue", type=int, default=100000)
-ap.add_argument("--ctas-per-sm", type=int, default=0); ap.add_argument("--distribution", type=int, default=2)
+ap.add_argument("--ctas-per-sm", type=int, default=0); ap.add_argument("--no-timers", action="store_true"); ap.add_argument("--distribution", type=int, default=2)
 a = ap.parse_args()
 p = pkg.default_params(nUE=a.nue, distribution=a.distribution)
-with pkg.RachSim([p], reps=a.reps, devices=[0], ctas_per_sm=a.ctas_per_sm) as sim:
+with pkg.RachSim([p], reps=a.reps, devices=[0], ctas_per_sm=a.ctas_per_sm, phase_timers=not a.no_timers) as sim:
     sim.run(); sim.run()
     cyc = sim.phase_cycles().astype(float)
     names = ["0 setup", "1 events", "2 c3", "3 uncertain", "4 late", "5 scans", "6 grants", "7 apply", "8", "9"]
