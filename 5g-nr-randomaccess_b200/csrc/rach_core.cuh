@@ -56,11 +56,14 @@ typedef unsigned long long ra_u64;
 #define RA_SCAP  2048       /* singleton scans of one ms kept in shared memory  */
 #endif
 #define RA_MAGIC5 858993460u /* ra_magic(5) */
+/* Optional shared-memory front of the per-ms work lists.  Measured on B200 with 1024 / 256 entries
+ * (+20 KB per block): 12 % SLOWER than leaving the lists in the block's global workspace (L2-resident):
+ * the smaller L1 costs more than the shorter small phases gain.  Default: all in global memory. */
 #ifndef RA_LCAP
-#define RA_LCAP  1024       /* re-transmitters of one ms kept in shared memory (rest: global) */
+#define RA_LCAP  0          /* re-transmitters of one ms kept in shared memory (rest: global) */
 #endif
 #ifndef RA_UCAP
-#define RA_UCAP  256        /* uncertain movers of one ms kept in shared memory (rest: global) */
+#define RA_UCAP  0          /* uncertain movers of one ms kept in shared memory (rest: global) */
 #endif
 
 /* ---- atomics: CUDA on the device, plain read-modify-write in the host emulator ---------- */
