@@ -172,12 +172,13 @@ RA_HD unsigned ra_first_scan(const RaShared& s, unsigned p) {     /* s[p] of the
 
 /* per-ms work lists: the first entries live in shared memory (the small phases then never wait for
  * L2), the overflow in the block's global workspace */
-RA_HD uint4 ra_lrec_get(const RaWork& w, const RaShared& s, unsigned l) { return l < RA_LCAP ? s.sLand[l] : w.landerRec[l]; }
-RA_HD unsigned ra_lmeta_get(const RaWork& w, const RaShared& s, unsigned l) { return l < RA_LCAP ? s.sLandMeta[l] : w.landerMeta[l]; }
-RA_HD void ra_lmeta_set(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l < RA_LCAP) s.sLandMeta[l] = v; else w.landerMeta[l] = v; }
-RA_HD void ra_lmeta_add(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l < RA_LCAP) RA_AADD(&s.sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
-RA_HD void ra_unc_set(const RaWork& w, RaShared& s, unsigned u, const uint4& e) { if (u < RA_UCAP) s.sUnc[u] = e; else w.uncertain[u] = e; }
-RA_HD uint4 ra_unc_get(const RaWork& w, const RaShared& s, unsigned u) { return u < RA_UCAP ? s.sUnc[u] : w.uncertain[u]; }
+/* (x + 1 <= cap instead of x < cap: no "pointless comparison" diagnostics when a capacity is 0) */
+RA_HD uint4 ra_lrec_get(const RaWork& w, const RaShared& s, unsigned l) { return l + 1 <= RA_LCAP ? s.sLand[l] : w.landerRec[l]; }
+RA_HD unsigned ra_lmeta_get(const RaWork& w, const RaShared& s, unsigned l) { return l + 1 <= RA_LCAP ? s.sLandMeta[l] : w.landerMeta[l]; }
+RA_HD void ra_lmeta_set(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) s.sLandMeta[l] = v; else w.landerMeta[l] = v; }
+RA_HD void ra_lmeta_add(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) RA_AADD(&s.sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
+RA_HD void ra_unc_set(const RaWork& w, RaShared& s, unsigned u, const uint4& e) { if (u + 1 <= RA_UCAP) s.sUnc[u] = e; else w.uncertain[u] = e; }
+RA_HD uint4 ra_unc_get(const RaWork& w, const RaShared& s, unsigned u) { return u + 1 <= RA_UCAP ? s.sUnc[u] : w.uncertain[u]; }
 
 /* append a record to move bucket `m`; returns its position */
 RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
@@ -218,7 +219,7 @@ RA_HD void ra_msg3_push(const RaWork& w, RaShared& s, int due, const uint4& rec)
 RA_HD void ra_lander_push(const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
     unsigned l = RA_AADD(&s.nLanders, 1u);
     if (l >= (unsigned)w.cap) { s.overflow = 1; return; }
-    if (l < RA_LCAP) { s.sLand[l] = rec; s.sLandMeta[l] = member; }
+    if (l + 1 <= RA_LCAP) { s.sLand[l] = rec; s.sLandMeta[l] = member; }
     else { w.landerRec[l] = rec; w.landerMeta[l] = member; }
 }
 
