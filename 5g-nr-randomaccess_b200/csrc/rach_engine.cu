@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -463,6 +464,8 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
                            : (dump ? (const void*)ra_step_kernel<true> : (const void*)ra_step_kernel<false>);
     RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
+    if (const char* cv = getenv("RACH_CARVEOUT"))      /* tuning aid: shared-memory carveout in percent */
+        RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     int occ = 0;
     RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RA_NT, d.smem));
     if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
