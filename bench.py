@@ -234,6 +234,9 @@ def run_our_arm(args):
                 "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": 8 + 0,
                         "d2h_bytes_per_step": stats_bytes + 4},
                 "gpu_launches": launches * world,
+                # BASELINE.md section 1 has no published throughput; the only timing the reference ships is
+                # results.csv column 6 (unknown hardware, -O0): 370.5 s for the 100k-UE point = 5.4e5 updates/s
+                "vs_results_csv_derived": value / world / 5.4e5,
                 "kernel_ms_per_step": kernel_ms / args.steps,
                 "replications_per_s": reps_total * args.steps / (kernel_ms / 1e3),
                 "clocks": clocks,
