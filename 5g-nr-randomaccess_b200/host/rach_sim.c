@@ -6,7 +6,13 @@
  *     (and their long forms); same validation messages, same exit status (255), same help text
  *     on an unknown flag (W:159-204).  The README spells some of them -r -m -u; those are
  *     accepted here as aliases (a superset; the reference itself rejects them).
- *   added:  --nue a,b,c  (points; default the reference sweep 10000..100000 step 10000, W:221)
+ *   added:  --format w|b|n  report layout: w (default) RandomAccessWithNOMA.c:354-366,731-825;
+ *                           b = RandomAccessSimulatorBeta.c:200-209,432-514 (54 grants by default, no
+ *                               activation draws, its own counters and file names, a "Latency" line / 6th
+ *                               file line that carries the kernel time of the whole launch);
+ *                           n = NOMA.c:598-635,712-716 (variant N: "nUE nSuccess ratio meanTx meanDelay",
+ *                               appended to TestResults/Sector_<nUE>_Result.txt, "Done" after each seed)
+ *           --nue a,b,c  (points; default the reference sweep 10000..100000 step 10000, W:221)
  *           --no-logs    (skip the per-UE *_Logs.txt, W:797-825)
  *           --outdir DIR (default "."), --device N, --seed64 S (tape key, default 0)
  *
@@ -61,7 +67,8 @@ static int is_flag(const char* a, const char* l, const char* s, const char* alia
 int main(int argc, char* argv[]) {
     ra_params base;
     ra_params_default(&base, RA_VARIANT_W);
-    int times = 1, writeLogs = 1, device = 0;
+    int times = 1, writeLogs = 1, device = 0, grantSet = 0;
+    char format = 'w';
     const char* outdir = ".";
     int nueList[64], nNue = 0;
     unsigned long long seed64 = 0;
@@ -84,7 +91,7 @@ int main(int argc, char* argv[]) {
             base.backoffIndicator = atoi(v);
         } else if (is_flag(a, "--grant", "-g", NULL)) {
             if (atoi(v) < 1) die("The number of Up Link Grant per RAR must be greater than zero.");
-            base.nGrantUL = atoi(v);
+            base.nGrantUL = atoi(v); grantSet = 1;
         } else if (is_flag(a, "--rarCount", "-rc", "-r")) {
             if (atoi(v) < 1) die("The maximum RAR window size must be greater than zero.");
             base.maxRarWindow = atoi(v) + 1;                                                  /* W:128 */
@@ -107,6 +114,7 @@ int main(int argc, char* argv[]) {
             char* dup = strdup(v);
             for (char* tok = strtok(dup, ","); tok && nNue < 64; tok = strtok(NULL, ",")) nueList[nNue++] = atoi(tok);
             free(dup);
+        } else if (strcmp(a, "--format") == 0) { format = v[0];
         } else if (strcmp(a, "--outdir") == 0) { outdir = v;
         } else if (strcmp(a, "--device") == 0) { device = atoi(v);
         } else if (strcmp(a, "--seed64") == 0) { seed64 = strtoull(v, NULL, 0);
@@ -114,14 +122,24 @@ int main(int argc, char* argv[]) {
     }
     if (nNue == 0) for (int n = 10000; n <= 100000; n += 10000) nueList[nNue++] = n;   /* W:221 */
     base.seed = seed64;
+    if (format != 'w' && format != 'b' && format != 'n') usage_and_exit();
+    if (format == 'b') { base.geometry = 0; if (!grantSet) base.nGrantUL = 54; }         /* B:49, B:137-145 */
+    if (format == 'n') {                                                                 /* NOMA.c:41-57 */
+        ra_params n; ra_params_default(&n, RA_VARIANT_N);
+        n.nPreamble = base.nPreamble; n.backoffIndicator = base.backoffIndicator; n.accessTime = base.accessTime;
+        if (grantSet) n.nGrantUL = base.nGrantUL;
+        n.seed = seed64; base = n; writeLogs = 0;
+    }
 
     const int uniform = base.distribution == 1;
-    printf(uniform ? "Traffic model: Uniform\n\n" : "Traffic model: Beta\n\n");          /* W:208-213 */
+    if (format != 'n') printf(uniform ? "Traffic model: Uniform\n\n" : "Traffic model: Beta\n\n");   /* W:208-213, B:59-64 */
 
     char dir[600];
-    snprintf(dir, sizeof dir, "%s/%s", outdir, uniform ? "NomaUniformResults" : "NomaBetaResults");
+    snprintf(dir, sizeof dir, "%s/%s", outdir, format == 'n' ? "TestResults" :
+             format == 'b' ? (uniform ? "BasicUniformSimulationResults" : "BasicBetaSimulationResults")
+                           : (uniform ? "NomaUniformResults" : "NomaBetaResults"));
     mkdir(outdir, 0755);
-    mkdir(dir, 0755);                                                                    /* W:67-68 */
+    mkdir(dir, 0755);                                                                    /* W:67-68; README.md:6-10 for B */
 
     ra_params* pts = (ra_params*)calloc((size_t)nNue, sizeof *pts);
     for (int k = 0; k < nNue; ++k) { pts[k] = base; pts[k].nUE = nueList[k]; }
@@ -155,6 +173,20 @@ int main(int argc, char* argv[]) {
             } else {
                 totalDelay = (float)st.delaySum;                 /* identical while the sum stays below 2^24 */
             }
+            if (format == 'n') {                                 /* NOMA.c:598-635 */
+                char path[800];
+                snprintf(path, sizeof path, "%s/Sector_%d_Result.txt", dir, nUE);
+                FILE* fp = fopen(path, "a");
+                if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
+                char line[256];
+                snprintf(line, sizeof line, "%d %d %lf %lf %lf\n", nUE, st.nSuccess, ((float)st.nSuccess / (float)nUE) * 100.0,
+                         ((float)(int)st.preambleTxSum / (float)st.nSuccess), ((float)(int)st.delaySum / (float)st.nSuccess));
+                fputs(line, stdout); fputs(line, fp);
+                fclose(fp);
+                free(ue);
+                if (k == nNue - 1) printf("Done\n");             /* NOMA.c:716 */
+                continue;
+            }
             const int nSuccessUE = st.nSuccess, failedUEs = nUE - nSuccessUE;
             const int preambleTxCount = (int)st.preambleTxSum;
             const int continueFailed = (int)st.continueFailed, finalSuccess = (int)st.finalSuccess;
@@ -162,18 +194,20 @@ int main(int argc, char* argv[]) {
 
             printf("-------- %05d Result ---------\n", activeCheck);                     /* W:354 */
             if (uniform) printf("Number of RA try UEs per Subframe: %d\n", nAccessUE);   /* W:355-357 */
-            printf("Fail Counts: %d\n", (int)st.failCountSum);                           /* W:361 */
+            const double latency = ra_sim_kernel_ms(sim) / 1e3;   /* B:205-206: cumulative clock(); here the whole launch */
+            if (format == 'b') printf("Latency: %lf\n", latency);
+            else printf("Fail Counts: %d\n", (int)st.failCountSum);                      /* W:361 */
 
             /* W:735-739 */
             float ratioSuccess = (float)nSuccessUE / (float)nUE * 100.0;
-            float nCollisionPreambles = (float)st.collisionPreambles / ((float)nUE * (float)nPreamble);
+            float nCollisionPreambles = (float)(format == 'b' ? st.collisionScans : st.collisionPreambles) / ((float)nUE * (float)nPreamble);   /* B:349 vs W:650 */
             float averagePreambleTx = (float)preambleTxCount / (float)nSuccessUE;
             float averageDelay = totalDelay / (float)nSuccessUE;
             printf("Number of UEs: %d\n", nUE);
             printf("Total simulation time: %dms\n", st.simTimeMs);
             printf("Success ratio: %.2lf\n", ratioSuccess);
             printf("Number of succeed UEs: %d\n", nSuccessUE);
-            printf("Number of falied UEs: %d\n", continueFailed);
+            if (format == 'w') printf("Number of falied UEs: %d\n", continueFailed);
             printf("Number of collision preambles: %.6lf\n", nCollisionPreambles);
             printf("Average preamble tx count: %.2lf\n", averagePreambleTx);
             printf("Average delay: %.2lf\n", averageDelay);
@@ -183,13 +217,17 @@ int main(int argc, char* argv[]) {
             FILE* fp = fopen(path, "w+");
             if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
             fprintf(fp, "%d\n%.2lf\n%d\n%.2lf\n%.2lf\n", nUE, ratioSuccess, nSuccessUE, averagePreambleTx, averageDelay);
-            fprintf(fp, "Number of total preamble tx: %d\n", preambleTxCount);
-            fprintf(fp, "Finally Falied: %d\n", continueFailed);
-            fprintf(fp, "Finally Success: %lf\n", (float)finalSuccess / (float)(continueFailed + finalSuccess));
+            if (format == 'b') fprintf(fp, "%lf", latency);                              /* B:481 */
+            else {
+                fprintf(fp, "Number of total preamble tx: %d\n", preambleTxCount);
+                fprintf(fp, "Finally Falied: %d\n", continueFailed);
+                fprintf(fp, "Finally Success: %lf\n", (float)finalSuccess / (float)(continueFailed + finalSuccess));
+            }
             fclose(fp);
 
             if (writeLogs) {                                                             /* W:797-825 */
-                snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.txt", dir, seed, nPreamble, nUE);
+                if (format == 'b' && uniform) snprintf(path, sizeof path, "%s/%d_Exclude_msg2_failures_UE%05d_Logs.txt", dir, nPreamble, nUE);   /* B:488 */
+                else snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.txt", dir, seed, nPreamble, nUE);
                 fp = fopen(path, "w+");
                 if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
                 static const char* names[15] = {"Idx", "Timer", "Active", "txTime", "FirstTxTime", "SecondTxTime", "NowBackoff",
