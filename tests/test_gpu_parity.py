@@ -129,6 +129,17 @@ def test_full_size_100k_uniform(pkg, oracle):
     assert st.nSuccess == 100000 and st.simTimeMs < 60000
 
 
+def test_beyond_the_reference_sweep_300k(pkg, oracle):
+    """Three times the largest size the reference sweeps (W:221), 64 preambles / 16 grants / BI 40 (the corner of
+    BASELINE configs[4]): every UE and every counter."""
+    kw = dict(nUE=300000, nPreamble=64, nGrantUL=16, backoffIndicator=40, seed=11, rep=2)
+    res, ue_ref, _ = oracle.run_port(oracle.make_config(**kw))
+    st, ue, _ = _run_gpu(pkg, kw)
+    for k in KEYS:
+        assert getattr(st, k) == getattr(res, k), k
+    np.testing.assert_array_equal(ue, ue_ref)
+
+
 def test_batch_is_placement_invariant(pkg, oracle):
     """Many replications and two parameter points in one launch == each alone (keyed tape);
     dump on/off and the CTAs-per-SM setting do not change any counter."""
