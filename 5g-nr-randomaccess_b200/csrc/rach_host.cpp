@@ -16,9 +16,11 @@
 
 #define betaF 0.0165
 
-/* W:844-847 */
+/* W:844-847.  The reference is C: pow() takes doubles whatever the argument types.  This file is C++,
+ * where pow(float, float) would select the float overload and change ceil() of the quotient below for
+ * some nUE (caught at nUE = 300000) -- hence the explicit promotions. */
 static float ra_beta_dist(float a, float b, float x) {
-    float betaValue = (1 / betaF) * (pow(x, (a - 1))) * (pow((1 - x), (b - 1)));
+    float betaValue = (1 / betaF) * (pow((double)x, (double)(a - 1))) * (pow((double)(1 - x), (double)(b - 1)));
     return betaValue;
 }
 

@@ -289,5 +289,25 @@ int oracle_run(const ref_config* cfg, ref_result* res, int* perUE, float* geom) 
     return 0;
 }
 
+/* the Beta arrival counts of W:285-287 alone (C semantics), for the host-schedule test */
+int oracle_beta_arrivals(int nUE, int accessTime, int* perMs /* [10000] */) {
+    const int maxTime = 10000;
+    int activeCheck = 0, allAt = -1;
+    for (int time = 0; time < maxTime; ++time) {
+        perMs[time] = 0;
+        if (activeCheck >= nUE) activeCheck = nUE;
+        if (time % accessTime == 0 && activeCheck != nUE) {
+            const int before = activeCheck;
+            float betaDist = o_beta_dist(3, 4, (float)time / (float)maxTime);
+            int accessUEs = (int)ceil((float)nUE * betaDist / ((float)maxTime / (float)accessTime));
+            activeCheck += accessUEs;
+            if (activeCheck >= nUE) activeCheck = nUE;
+            perMs[time] = activeCheck - before;
+            if (activeCheck == nUE && allAt < 0) allAt = time;
+        }
+    }
+    return allAt;
+}
+
 int oracle_sizeof_config(void) { return (int)sizeof(ref_config); }
 int oracle_sizeof_result(void) { return (int)sizeof(ref_result); }

@@ -86,3 +86,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".c")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_beta_schedule_equals_the_c_expression_for_many_sizes(pkg, oracle):
+    """ra_arrival_schedule (C++ host code of the product) against the reference's C expression
+    (W:285-287, 844-847) for 400 population sizes and three subframe lengths.  Guards the C-vs-C++
+    pow() overload trap: pow(float, float) in C++ is powf and moves ceil() for some nUE."""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "librach_oracle.so"))
+    lib.oracle_beta_arrivals.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    ref = np.zeros(10000, dtype=np.int32)
+    sizes = list(range(1000, 100001, 1000)) + list(range(105000, 1000001, 5000)) + [1, 7, 54321, 300000, 999983]
+    for a in (5, 7, 10):
+        for n in sizes if a == 5 else sizes[::7]:
+            at_ref = lib.oracle_beta_arrivals(n, a, ref.ctypes.data_as(C.c_void_p))
+            arr, at = pkg.arrival_schedule(pkg.default_params(nUE=n, accessTime=a))
+            assert at == at_ref and np.array_equal(arr, ref), (n, a)
