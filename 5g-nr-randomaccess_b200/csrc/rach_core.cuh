@@ -51,7 +51,9 @@ typedef unsigned long long ra_u64;
 #define RA_DEAD  0xFFFFFFFFu
 #define RA_M3RING 64
 #define RA_DUMP_W 16
+#ifndef RA_HBINS
 #define RA_HBINS 1024       /* histogram bins of the grant selection            */
+#endif
 #ifndef RA_SCAP
 #define RA_SCAP  2048       /* singleton scans of one ms kept in shared memory  */
 #endif
