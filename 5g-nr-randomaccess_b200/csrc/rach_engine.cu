@@ -226,7 +226,7 @@ static size_t rn_smem_bytes(int R, int P) {
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel_n(RaKernelArgs a) {
+__global__ void __launch_bounds__(RA_NT, 4) ra_step_kernel_n(RaKernelArgs a) {     /* fp64 activation math: 64 registers, no spills */
     extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
     __shared__ RaSharedN s;
     __shared__ RaPointDev sPt;
