@@ -318,23 +318,21 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     const bool limit = (int)mrc >= pt.M;
     /* both branches draw the backoff: retry W:540 (1st draw), limit W:514 (2nd draw) */
     const int tmp = (int)ra_mod((limit ? d.v[1] : d.v[0]) >> 1, (unsigned)pt.BI, pt.magicBI);
-    unsigned pnew = p0, z = rec.z;
-    int base = T;                                           /* retry: subTime = time + tmp, W:542 */
-    if (limit) {
-        /* limit branch, W:498-531: new preamble, counters reset, subTime = CURRENT txTime + tmp (W:516):
-         * an old txTime if stale, T+1 if a lower index postponed me (certain above the leader),
-         * T under the not-postponed hypothesis if uncertain (settled in phase 3) */
-        acc.contFailed++;
-        pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
-        const unsigned fail = ra_rec_fail(rec) + 1;
-        if (fail > 0xFFFFu) s.overflow = 2;
-        z = ra_z((unsigned)T, fail); mrc = 0; ptc = 1;
-        base = stale ? (int)rec.y : (uncertain ? T : T + 1);
-    } else {
-        /* retry branch, W:532-558 */
-        mrc++; ptc++;
-        if (ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
-    }
+    /* Both branches written as selects: one mover in ten takes the limit branch, so almost every warp would
+     * otherwise execute both sides of an if/else.
+     *   retry branch, W:532-558: subTime = time + tmp (W:542); maxRarCounter++, preambleTxCounter++
+     *   limit branch, W:498-531: new preamble, counters reset, timer = 0, failCount++, subTime = CURRENT
+     *     txTime + tmp (W:516): an old txTime if stale, T+1 if a lower index postponed me (certain above the
+     *     leader), T under the not-postponed hypothesis if uncertain (settled in phase 3) */
+    const unsigned pl = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
+    const unsigned pnew = limit ? pl : p0;
+    const unsigned fail = ra_rec_fail(rec) + (limit ? 1u : 0u);
+    const unsigned z = limit ? ra_z((unsigned)T, fail) : rec.z;
+    mrc = limit ? 0u : mrc + 1u;
+    ptc = limit ? 1u : ptc + 1u;
+    acc.contFailed += limit ? 1u : 0u;
+    const int base = limit ? (stale ? (int)rec.y : (uncertain ? T : T + 1)) : T;
+    if (fail > 0xFFFFu || ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
     const int X = ra_align(base + tmp, pt.A, pt.magicA);
     const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
     if (uncertain) {
