@@ -1,7 +1,7 @@
 /*
  * rach_core.cuh -- the per-replication RACH engine (variant W/B dynamics), written once as
  * "phase" functions that a CUDA thread block executes with __syncthreads() between them
- * (rach_kernels.cu).  tests/emu/ compiles the same phases for the host and runs them thread
+ * (rach_engine.cu).  tests/emu/ compiles the same phases for the host and runs them thread
  * by thread (test infrastructure only; the product library has no CPU path).
  *
  * WHAT IT COMPUTES: exactly the per-ms state machine of RandomAccessWithNOMA.c:267-335
