@@ -18,6 +18,9 @@
  *     preamble and an aligned backoff; a restart whose txTime is not after the current ms can
  *     never transmit again in the reference (txTime == time+1 is tested only at occasions):
  *     such a UE becomes a "zombie" (kept only for the per-UE dump).
+ * pt.geometry == 0 selects NOMA.c's alternative, non-sector collision function (N:325-447; its call is commented
+ * out at N:688): one grant counter for the whole cell, no sector buckets, a lone singleton is always answered
+ * (N:377-384), one base-station draw per granted pair and p < 0.3 answers only the weaker UE (N:411-415).
  * timer / nowBackoff are derived from (timerStart, txTime) as in variant W.
  * fp64 follows the C semantics of the reference (float locals, double libm); products and sums
  * that C would not fuse are written with explicit round-to-nearest intrinsics on the device.
@@ -173,7 +176,7 @@ RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int
 /* ---- occasion phase A2: histogram of the transmitters, N:206-226 ---- */
 RA_HD void rn_phaseA2_item(const RaPointDev& pt, const RaWorkN& w, RaSharedN& s, int T, unsigned j) {
     const uint4 r = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + j];
-    const unsigned k = rn_sector(r) * (unsigned)pt.P + rn_p(r);
+    const unsigned k = (pt.geometry ? rn_sector(r) : 0u) * (unsigned)pt.P + rn_p(r);
     if (RA_AADD(&s.cnt[k], 1u) == 0) s.who[k] = j;
 }
 
@@ -193,8 +196,9 @@ RA_HD void rn_phaseB_sector(const RaJob& job, const RaWorkN& w, RaSharedN& s, in
         }
     if (count == 0) return;
     int grants = 0;
-    if (count <= G) {                                       /* N:252-260 */
-        for (int i = 0; i < count; ++i) if (grants < G) { grants++; s.grant[sec * P + sPos[i]] = 1; }
+    const bool nonSector = pt.geometry == 0;
+    if (count <= G) {                                       /* N:252-260; N:377-384 answers every lone singleton */
+        for (int i = 0; i < count; ++i) if (grants < G || nonSector) { grants++; s.grant[sec * P + sPos[i]] = 1; }
         return;
     }
     for (int i = 1; i < count; ++i) {                       /* sortUE N:90-103 == stable ascending sort */
@@ -218,8 +222,11 @@ RA_HD void rn_phaseB_sector(const RaJob& job, const RaWorkN& w, RaSharedN& s, in
                     const int r0 = rach_tape_rand31(pt.seed, job.rep, (unsigned)sec, (unsigned)T, bsK++, RACH_TAPE_TAG_BS);
                     const double pr = (double)r0 / (double)2147483647;                         /* N:284 */
                     if (pr < 0.3) {
-                        const int r1 = rach_tape_rand31(pt.seed, job.rep, (unsigned)sec, (unsigned)T, bsK++, RACH_TAPE_TAG_BS);
-                        s.grant[sec * P + ((r1 % 2) ? pj_ : pi_)] = 1;                         /* N:286-287 */
+                        if (nonSector) s.grant[sec * P + pi_] = 1;                             /* N:413-415 */
+                        else {
+                            const int r1 = rach_tape_rand31(pt.seed, job.rep, (unsigned)sec, (unsigned)T, bsK++, RACH_TAPE_TAG_BS);
+                            s.grant[sec * P + ((r1 % 2) ? pj_ : pi_)] = 1;                     /* N:286-287 */
+                        }
                     } else { s.grant[sec * P + pi_] = 1; s.grant[sec * P + pj_] = 1; }         /* N:290-291 */
                 }
                 break;
@@ -236,7 +243,7 @@ template <bool DUMP>
 RA_HD void rn_phaseC_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, unsigned j) {
     const RaPointDev& pt = *job.pt;
     uint4 r = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + j];
-    const unsigned idx = r.x, k = rn_sector(r) * (unsigned)pt.P + rn_p(r);
+    const unsigned idx = r.x, k = (pt.geometry ? rn_sector(r) : 0u) * (unsigned)pt.P + rn_p(r);
     if (s.cnt[k] == 1 && s.grant[k]) {                      /* msg2 == 1: N:491-497 */
         r.y = (unsigned)(T + 1 + 10);
         if (DUMP) { int* row = job.dump + (size_t)idx * RA_DUMP_W; row[4] = T + 11; }

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(RA_NT, 4) ra_step_kernel_n(RaKernelArgs a) {  
                 const unsigned nTx = s.bcount[(unsigned)T & Rm];
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
                 __syncthreads();
-                if ((tid & 31) == 0 && (tid >> 5) < RA_NSECT) rn_phaseB_sector(job, w, s, T, tid >> 5);
+                if ((tid & 31) == 0 && (tid >> 5) < (pt.geometry ? RA_NSECT : 1)) rn_phaseB_sector(job, w, s, T, tid >> 5);
                 __syncthreads();
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseC_item<DUMP>(job, w, s, T, j);
                 __syncthreads();

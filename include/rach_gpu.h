@@ -45,7 +45,9 @@ extern "C" {
                              raFailed nowBackoff 0 0 0 */
 #define RA_VARIANT_N  2   /* NOMA.c sector / gain-pairing dynamics (N:131-324, 449-566, 665-711):
                              nGrantUL = grants per sector (N:43), maxRarWindow <= 5 (N:45),
-                             maxMsg2TxCount carries maxMsg1ReTx (N:46), cellRadius (N:56), Beta only */
+                             maxMsg2TxCount carries maxMsg1ReTx (N:46), cellRadius (N:56), Beta only;
+                             geometry = 0 selects NOMA.c's alternative non-sector collision function
+                             (N:325-447, call commented out at N:688) */
 
 #define RA_OK            0
 #define RA_E_INVAL      -1   /* bad argument / unsupported parameter value */

@@ -63,6 +63,21 @@ SWEEP='s/for (int n = 10000; n <= 100000; n += 10000)/for (int n = ref_nue; n <=
   echo; echo '#include "ref_shim_post_n.h"'
 } | $CC $CFLAGS -x c - -o "$out/libref_n.so" -lm
 
+# ---- N2: NOMA.c with its alternative, non-sector collision function switched in -----------
+#   N:688-689  the commented-out call of preambleCollisionDetection (N:325-447) replaces the sector one
+#   N:325-447  its rand() (N:411, `user` is the array) -> base-station stream, sector 0
+{ echo '#include "ref_shim_pre.h"'
+  sed -e '644s/seed < 10/seed < 1/' \
+      -e '648s/for (int nUE = 10000; nUE <= 100000; nUE += 10000)/for (int nUE = ref_nue; nUE <= ref_nue; nUE += 10000)/' \
+      -e '499,546s/rand()/ref_tape_rand((user + i)->idx, time)/g' \
+      -e '194,324s/rand()/ref_tape_rand_bs(s, time)/g' \
+      -e '325,447s/rand()/ref_tape_rand_bs(0, time)/g' \
+      -e '688s#// preambleCollisionDetection#preambleCollisionDetection#' \
+      -e '689s#preambleSectorCollisionDetection#// preambleSectorCollisionDetection#' \
+      "$ref/NOMA.c"
+  echo; echo '#include "ref_shim_post_n.h"'
+} | $CC $CFLAGS -x c - -o "$out/libref_n2.so" -lm
+
 # ---- U0: RandomAccessSimulator.c ----------------------------------------------------------
 #   U0:42  nUE sweep -> ref_nue;  U0:48-49 parameter locals -> ref_p_*
 #   U0:84  `i <= activeCheck` reads one element past the array once activeCheck reaches nUE -> clamp

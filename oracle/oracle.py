@@ -67,7 +67,7 @@ def build(force=False):
         subprocess.check_call(["make", "-C", HERE, "_build/librach_oracle.so"],
                               stdout=subprocess.DEVNULL)
     have_ref = all(os.path.exists(os.path.join(HERE, "_ref", f))
-                   for f in ("libref_w.so", "libref_b.so", "libref_n.so", "libref_u0.so"))
+                   for f in ("libref_w.so", "libref_b.so", "libref_n.so", "libref_n2.so", "libref_u0.so"))
     if os.path.isdir("/root/reference") and (force or not have_ref):
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
@@ -135,8 +135,9 @@ def _run_n(f, cfg):
 
 
 def run_ref_n(cfg):
-    """NOMA.c itself in tape mode -> (result, per-UE ints [n,16] in N_DUMP_FIELDS order, channelGain [n])."""
-    path = os.path.join(HERE, "_ref", "libref_n.so")
+    """NOMA.c itself in tape mode -> (result, per-UE ints [n,16] in N_DUMP_FIELDS order, channelGain [n]).
+    cfg.geometry == 0: the build with NOMA.c's alternative non-sector collision function switched in."""
+    path = os.path.join(HERE, "_ref", "libref_n.so" if cfg.geometry else "libref_n2.so")
     if not os.path.exists(path):
         raise FileNotFoundError(path)
     return _run_n(_lib(path, "ref_run"), cfg)

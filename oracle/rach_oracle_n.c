@@ -6,6 +6,9 @@
  * betaDist N:563-566 -- driven by the Philox draw tape (include/rach_tape.h): UE draws keyed
  * (ue, ms, k), the base-station draws of N:284/286 keyed (sector, ms, k) with RACH_TAPE_TAG_BS.
  *
+ * cfg->geometry == 0 selects NOMA.c's alternative, non-sector collision function (N:325-447, its call is
+ * commented out at N:688): one grant counter per occasion, no sector buckets, one base-station draw per pair.
+ *
  * PARITY PIN: validated field by field (16 ints + channelGain of every UE) against NOMA.c itself
  * compiled in tape mode (oracle/_ref/libref_n.so, build_ref.sh) by tests/test_oracle_vs_reference.py.
  * Only tests/, smoke() and bench.py's CPU legs may load this.
@@ -107,6 +110,8 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
     const int maxTime = 10000;
     int activeCheck = 0, arrived = 0, nSuccess = 0, time;
     int sectorGrants[6];
+    const int nonSector = (cfg->geometry == 0);
+    const int nSect = nonSector ? 1 : 6;
 
     for (time = 0; time < maxTime; time++) {
         res->lastMs = time;
@@ -123,18 +128,20 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
             for (int i = 0; i < activeCheck; ++i) {
                 nue* u = c.ue + i;
                 if (u->RA == 0 && u->txTime == time + 1 && u->msg2 == 0 && u->nowBackoff <= 0 && u->RaFailed == 0) {
-                    int k = u->sector * P + u->preamble;
+                    int k = (nonSector ? 0 : u->sector) * P + u->preamble;
                     if (cnt[k]++ == 0) who[k] = i;
                 }
             }
-            for (int s = 0; s < 6; ++s) {
+            for (int s = 0; s < nSect; ++s) {
                 int count = 0;
                 for (int p = 0; p < P; ++p)                 /* singles in preamble order, N:243-249 */
                     if (cnt[s * P + p] == 1) { tx[count].idx = who[s * P + p]; tx[count].gain = c.ue[who[s * P + p]].channelGain; count++; }
                 if (count == 0) continue;
-                if (count <= G) {                           /* N:252-260 */
-                    for (int i = 0; i < count; ++i)
+                if (count <= G) {                           /* N:252-260; N:377-384 grants msg2 unconditionally */
+                    for (int i = 0; i < count; ++i) {
                         if (sectorGrants[s] < G) { sectorGrants[s]++; c.ue[tx[i].idx].msg2 = 1; }
+                        else if (nonSector) c.ue[tx[i].idx].msg2 = 1;
+                    }
                 } else {
                     /* sortUE N:90-103: bubble sort ascending by gain == a stable sort */
                     for (int i = 1; i < count; ++i) {
@@ -154,8 +161,11 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
                                     sectorGrants[s]++;
                                     double p = (double)n_rand_bs(&c, s, time) / (double)2147483647;
                                     if (p < 0.3) {
-                                        int randomUE = n_rand_bs(&c, s, time) % 2;
-                                        c.ue[randomUE ? rx1 : rx0].msg2 = 1;
+                                        if (nonSector) c.ue[rx0].msg2 = 1;                 /* N:413-415 */
+                                        else {
+                                            int randomUE = n_rand_bs(&c, s, time) % 2;      /* N:286-287 */
+                                            c.ue[randomUE ? rx1 : rx0].msg2 = 1;
+                                        }
                                     } else { c.ue[rx0].msg2 = 1; c.ue[rx1].msg2 = 1; }
                                 }
                                 break;

@@ -56,6 +56,8 @@ N_CASES = [
     ("n_g1_p8_4000", dict(nUE=4000, nGrantUL=1, nPreamble=8, seed=3)),
     ("n_g4_bi40_sub10_8000", dict(nUE=8000, nGrantUL=4, backoffIndicator=40, accessTime=10, seed=4)),
     ("n_retx3_r100_6000", dict(nUE=6000, maxMsg2TxCount=3, cellRadius=100.0, seed=5)),
+    ("n_nonsector_8000", dict(nUE=8000, geometry=0, seed=6)),           # NOMA.c:325-447 switched in (N:688)
+    ("n_nonsector_g12_20000", dict(nUE=20000, geometry=0, nGrantUL=12, seed=7)),   # with the commented nGrantUL = 12 (N:687)
 ]
 
 U0_CASES = [

@@ -180,7 +180,7 @@ def test_error_paths(pkg):
 def _run_gpu_n(pkg, kw):
     kw = dict(kw)
     rep = kw.pop("rep", 0)
-    for k in ("useTape", "echo", "stopMs", "geometry", "distribution", "hBS", "hUT"):
+    for k in ("useTape", "echo", "stopMs", "distribution", "hBS", "hUT"):
         kw.pop(k, None)
     p = pkg.default_params(variant=2, **kw)
     with pkg.RachSim([p], reps=1, devices=[0], rep_offset=rep, dump_ues=True) as sim:
@@ -217,7 +217,7 @@ def test_noma_fuzz_against_oracle(pkg, oracle):
                           backoffIndicator=rnd.choice([1, 2, 20, 40]), nGrantUL=rnd.choice([1, 2, 4, 12]),
                           maxMsg2TxCount=rnd.choice([1, 3, 10]), accessTime=rnd.choice([5, 5, 6, 10]),
                           maxRarWindow=rnd.choice([3, 5]), cellRadius=rnd.choice([100.0, 500.0]),
-                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000)))
+                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000), geometry=rnd.choice([0, 1, 1])))
     for kw in cases:
         res, ue_ref, g_ref = oracle.run_port_n(oracle.make_config_n(**kw))
         st, ue, g = _run_gpu_n(pkg, kw)

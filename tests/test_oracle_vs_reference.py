@@ -74,7 +74,8 @@ def test_noma_variant_against_noma_c(oracle):
                           backoffIndicator=rnd.choice([1, 2, 20, 40]), nGrantUL=rnd.choice([1, 2, 4, 12]),
                           maxMsg2TxCount=rnd.choice([1, 3, 10]), accessTime=rnd.choice([5, 5, 6, 10]),
                           maxRarWindow=rnd.choice([3, 5]), cellRadius=rnd.choice([100.0, 500.0]),
-                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000)))
+                          seed=rnd.getrandbits(60), rep=rnd.randrange(1000), geometry=rnd.choice([0, 1])))
+    cases += [dict(nUE=9000, geometry=0, seed=5), dict(nUE=15000, geometry=0, nGrantUL=12, seed=6)]   # N:325-447 variant
     for kw in cases:
         cfg = oracle.make_config_n(**kw)
         r, ue, g = oracle.run_ref_n(cfg)
