@@ -52,10 +52,11 @@ typedef unsigned long long ra_u64;
 #define RA_M3RING 64
 #define RA_DUMP_W 16
 #ifndef RA_HBINS
-#define RA_HBINS 1024       /* histogram bins of the grant selection            */
+#define RA_HBINS 512        /* histogram bins of the grant selection            */
 #endif
 #ifndef RA_SCAP
-#define RA_SCAP  2048       /* singleton scans of one ms kept in shared memory  */
+#define RA_SCAP  512        /* singleton scans of one ms kept in shared memory (rest: global).  Shared memory is
+                               kept small on purpose: at 5 resident blocks x 48 registers the spills live in L1 */
 #endif
 #define RA_MAGIC5 858993460u /* ra_magic(5) */
 /* Optional shared-memory front of the per-ms work lists.  Measured on B200 with 1024 / 256 entries
@@ -97,6 +98,9 @@ struct RaWork {
     uint4*    uncertain;      /* [cap]  movers below the natural leader: pos, idx, p0|limit<<31 */
     uint4*    c3;             /* [cap]  limit movers that land iff not postponed: idx,p0,pnew,landed */
     unsigned* singles;        /* [cap]  UE index of every singleton scan of the ms          */
+    unsigned* minPos;         /* [R*P]  bucket position of each cohort's lowest UE -- a HINT (no atomic pair; verified on
+                                 use).  Global on purpose: 7 KB more shared memory per block shrinks L1 below the
+                                 register-spill working set of 5 resident blocks (measured: 10 % slower) */
     uint4*    e1Rec;          /* [cap3] Msg3 restarts that land on the current ms (W:693)   */
     unsigned* e1Meta;         /* [cap3] 1 = absorbed by a later scan                        */
     int cap, cap3;
@@ -114,7 +118,8 @@ struct RaShared {
     uint4*    sLand;          /* [RA_LCAP]  first re-transmitter records of the ms           */
     unsigned* sLandMeta;      /* [RA_LCAP]                                                   */
     uint4*    sUnc;           /* [RA_UCAP]  first uncertain movers of the ms                 */
-    int grantCheck, activeCheck, acOld, nArr, overflow, pad0;
+    int grantCheck, activeCheck, acOld, nArr, overflow, nextAc;   /* nextAc: activeCheck after the next arrival step */
+    int nextArrMs, occ;       /* next ms with T % A == 0 and its occasion number (no division in the ms loop) */
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant, nNl, pad1;
     ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
@@ -197,10 +202,12 @@ RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s
  * its RAR window expires at X + Wn - 1 (rarWindow is 1 at X, W:493) */
 RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec) {
     int m = (int)rec.y + pt.Wn - 1;
-    ra_bucket_push(pt, w, s, m, rec);
+    const unsigned pos = ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
     RA_AADD(&s.cnt[c], 1u);
-    if (rec.x < s.minI[c]) RA_AMIN(&s.minI[c], rec.x);   /* plain read first: the minimum rarely moves */
+    if (rec.x < s.minI[c]) {                              /* plain read first: the minimum rarely moves */
+        if (RA_AMIN(&s.minI[c], rec.x) > rec.x) w.minPos[c] = pos;
+    }
 }
 
 /* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old
@@ -256,6 +263,7 @@ RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
     if (tid == 0) {
         s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0;
+        s.nextAc = pt.arrCum[0]; s.nextArrMs = 0; s.occ = 0;
         s.nSuccess = 0; s.noGrant = 0;
         s.txSum = s.delaySum = s.failSum = s.contFailed = s.collP = s.txop = s.collScans = s.totScans = 0;
     }
@@ -281,10 +289,14 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
         s.l2[p] = RA_INF32; s.before[p] = 0; s.extraFirst[p] = 0; s.clsSize[p] = 0;
     }
     if (tid == 0) {
-        if (T % 5 == 0) s.grantCheck = 0;                       /* literal 5, W:268 */
+        if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) s.grantCheck = 0;          /* literal 5, W:268 */
         s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
         s.acOld = s.activeCheck;
-        if (T % pt.A == 0 && s.activeCheck != pt.nUE) s.activeCheck = pt.arrCum[T / pt.A];
+        if (T == s.nextArrMs) {                                                 /* T % accessTime == 0, W:280 */
+            if (s.activeCheck != pt.nUE) s.activeCheck = s.nextAc;
+            s.nextArrMs = T + pt.A; s.occ++;
+            if (s.occ < pt.nOcc) s.nextAc = pt.arrCum[s.occ];                   /* needed A ms from now: latency hidden */
+        }
         s.nArr = s.activeCheck - s.acOld;
         s.nMov = s.bcount[(unsigned)T & Rm];
         s.nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
@@ -602,6 +614,21 @@ __device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWor
 
 RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && idx <= s.tau; }
 
+/* a granted visible non-mover leaves its bucket and cohort and queues Msg3 (W:642-645) */
+template <bool DUMP>
+RA_HD void ra_grant_nonmover(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned q, unsigned slot, size_t at) {
+    const RaPointDev& pt = *job.pt;
+    uint4 rec = w.bucket[at];
+    w.bucket[at].x = RA_DEAD;
+    s.cnt[slot * pt.P + q] -= 1; s.minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
+    if (DUMP) {
+        int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
+        row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
+    }
+    rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
+    ra_msg3_push(w, s, T + 11, rec);
+}
+
 /* =========================================================================================
  * Phase 6 -- apply the outcomes of the scans (W:641-648, W:653-661), retire ms T.
  * items: [0,P) classes, [P, P+nLanders) landers, [.., +nE1) late restarts
@@ -614,8 +641,15 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
         const unsigned q = item;
         const unsigned sq = ra_first_scan(s, q);
         if (sq != RA_INF32 && sq == s.l1[q] && s.clsSize[q] == 1 && ra_granted(s, sq)) {
-            unsigned k = RA_AADD(&s.nNl, 1u);               /* handled by ra_phase6b (needs the record) */
-            s.nlList[k] = q;
+            /* a visible non-mover scanned alone and was granted: active=2, txTime=T+11, W:642-645.  Its record
+             * sits in the bucket of its move time, normally at the hinted position */
+            const unsigned slot = s.l1m[q], hint = w.minPos[slot * pt.P + q];
+            const size_t at = (size_t)slot * w.cap + hint;
+#ifndef RA_NO_POS_HINT
+            if (hint < s.bcount[slot] && w.bucket[at].x == sq) ra_grant_nonmover<DUMP>(job, w, s, T, q, slot, at);
+            else
+#endif
+            { unsigned k = RA_AADD(&s.nNl, 1u); s.nlList[k] = q; }      /* rare: found by ra_phase6b */
         }
         if (q == 0) { s.bcount[(unsigned)T & Rm] = 0; s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
         /* the cohort that moved in this ms is gone */
@@ -644,27 +678,18 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     }
 }
 
-/* Phase 6b (every thread, only if nNl > 0) -- a visible non-mover that scanned alone and was
- * granted: active=2, txTime=T+11, W:642-645.  Its record sits somewhere in the bucket of its
- * move time; find it by index, retire it from bucket and cohort, queue Msg3. */
+/* Phase 6b (every thread, only if nNl > 0) -- fallback for a granted visible non-mover whose position hint
+ * was stale (two UEs lowered the cohort minimum at the same time): find the record in the bucket of its move
+ * time by index. */
 template <bool DUMP>
 RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
-    const RaPointDev& pt = *job.pt;
     for (unsigned e = 0; e < s.nNl; ++e) {
         const unsigned q = s.nlList[e], slot = s.l1m[q], want = s.l1[q];
         const unsigned n = s.bcount[slot];
         for (unsigned j = tid; j < n; j += nt) {
             const size_t at = (size_t)slot * w.cap + j;
             if (w.bucket[at].x != want) continue;
-            uint4 rec = w.bucket[at];
-            w.bucket[at].x = RA_DEAD;
-            s.cnt[slot * pt.P + q] -= 1; s.minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
-            if (DUMP) {
-                int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
-                row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
-            }
-            rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
-            ra_msg3_push(w, s, T + 11, rec);
+            ra_grant_nonmover<DUMP>(job, w, s, T, q, slot, at);
         }
     }
 }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R
 
 static size_t ra_smem_bytes(int R, int P) {
     return sizeof(uint4) * (RA_LCAP + RA_UCAP) + sizeof(unsigned) * RA_LCAP +
-           sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
+           2 * sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
            sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P + sizeof(unsigned) * (RA_HBINS + RA_SCAP);
 }
 
@@ -465,8 +465,13 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
                            : (dump ? (const void*)ra_step_kernel<true> : (const void*)ra_step_kernel<false>);
     RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
-    if (const char* cv = getenv("RACH_CARVEOUT"))      /* tuning aid: shared-memory carveout in percent */
-        RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    /* ask for the largest shared-memory carveout: the residency computed below must be the real one (with the
+     * default heuristic a 35 KB block ran 4 per SM while the occupancy query said 5 -> late blocks, long tail) */
+    {
+        const char* cv = getenv("RACH_CARVEOUT");         /* tuning aid: carveout in percent */
+        RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cv ? atoi(cv) : (int)cudaSharedmemCarveoutMaxShared));
+    }
     int occ = 0;
     RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RA_NT, d.smem));
     if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
@@ -487,6 +492,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     const size_t oSingles = off;   if (!isN) off = ra_align_up(off + sizeof(unsigned) * cap, 256);
     const size_t oE1 = off;        if (!isN) off = ra_align_up(off + sizeof(uint4) * cap3, 256);
     const size_t oE1Meta = off;    if (!isN) off = ra_align_up(off + sizeof(unsigned) * cap3, 256);
+    const size_t oMinPos = off;    if (!isN) off = ra_align_up(off + sizeof(unsigned) * (size_t)sim->maxR * sim->maxP, 256);
     const size_t perBlock = off;
 
     size_t freeB = 0, totalB = 0;
@@ -521,7 +527,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
         w.landerRec = (uint4*)(base + oLander); w.landerMeta = (unsigned*)(base + oLMeta);
         w.uncertain = (uint4*)(base + oUnc); w.c3 = (uint4*)(base + oC3);
         w.singles = (unsigned*)(base + oSingles); w.e1Rec = (uint4*)(base + oE1);
-        w.e1Meta = (unsigned*)(base + oE1Meta); w.cap = sim->cap; w.cap3 = sim->cap3;
+        w.e1Meta = (unsigned*)(base + oE1Meta); w.minPos = (unsigned*)(base + oMinPos); w.cap = sim->cap; w.cap3 = sim->cap3;
     }
     RA_CUDA(sim, cudaMalloc(&d.dWorks, sizeof(RaWork) * grid));
     RA_CUDA(sim, cudaMemcpy(d.dWorks, works.data(), sizeof(RaWork) * grid, cudaMemcpyHostToDevice));

@@ -122,7 +122,9 @@ int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
 int ra_host_ring(const ra_params* p) {
     const int a = p->accessTime > 5 ? p->accessTime : 5;
     if (p->variant == RA_VARIANT_N) return next_pow2(p->backoffIndicator + a + 6);   /* occasion <= T + BI + A + 2 */
-    return next_pow2(p->backoffIndicator + a + p->maxRarWindow + 2);
+    /* largest distance from the current ms to a move time: limit branch from a postponed txTime,
+     * align(T+1+BI-1) + Wn-1 <= T + BI + A + Wn - 2 (Msg3 restart: T + BI + Wn + 2) -> R must exceed it */
+    return next_pow2(p->backoffIndicator + a + p->maxRarWindow);
 }
 
 /* arrCum[occ] = activeCheck after the arrival step of ms occ*accessTime */

@@ -53,8 +53,8 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
 
     RaShared s; memset(&s, 0, sizeof s);
     std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8), hist(RA_HBINS), sIdx(RA_SCAP);
-    std::vector<unsigned> minI((size_t)pt.R * pt.P);
-    s.cnt = cnt.data(); s.minI = minI.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
+    std::vector<unsigned> minI((size_t)pt.R * pt.P), minPos((size_t)pt.R * pt.P);
+    s.cnt = cnt.data(); s.minI = minI.data(); w.minPos = minPos.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
     s.N = cls.data(); s.l1 = s.N + pt.P; s.nlList = s.l1 + pt.P; s.l1m = s.nlList + pt.P; s.l2 = s.l1m + pt.P;
     s.hist = hist.data(); s.sIdx = sIdx.data();
     std::vector<uint4> sLand(RA_LCAP), sUnc(RA_UCAP); std::vector<unsigned> sLandMeta(RA_LCAP);

@@ -122,6 +122,7 @@ def test_work_list_overflow_paths(oracle, tmp_path):
     every run overflows them; results must not change."""
     so = str(tmp_path / "librach_emu_small.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DRA_LCAP=3", "-DRA_UCAP=2", "-DRA_SCAP=2",
+                           "-DRA_NO_POS_HINT",       # also: granted non-movers always take the search fallback (phase 6b)
                            "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"),
                            "-I", os.path.join(ROOT, "5g-nr-randomaccess_b200", "csrc"),
                            os.path.join(ROOT, "tests", "emu", "rach_emu.cpp"),
