@@ -36,6 +36,9 @@
                                  registers measured 3.8 % faster than 4 x 64 on the 4096-replication workload, 6 x 40 slower */
 #endif
 #define RA_NPHASE 10
+#ifndef RA_ILP
+#define RA_ILP 2             /* movers per thread and loop iteration (interleaved Philox chains) */
+#endif
 #define RA_U0_NT 8           /* variant U0: threads (= replications) per block; few, so the live lists stay in L1 */
 #define RA_TICK(k) do { if (timers && tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
@@ -122,18 +125,33 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
                 const uint4* bT = w.bucket + (size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap;
                 const uint4 dead = make_uint4(RA_DEAD, 0, 0, 0);
                 unsigned i = tid;
-                uint4 c0 = i < nMov ? bT[i] : dead;
-                uint4 c1 = i + nt < nMov ? bT[i + nt] : dead;
+#if RA_ILP >= 2
+                uint4 c[RA_ILP];
+#pragma unroll
+                for (int k = 0; k < RA_ILP; ++k) c[k] = i + k * nt < nMov ? bT[i + k * nt] : dead;
                 while (i < nMov) {
-                    const unsigned ni = i + 2 * nt;
-                    const uint4 n0 = ni < nMov ? bT[ni] : dead;
-                    const uint4 n1 = ni + nt < nMov ? bT[ni + nt] : dead;
-                    const rach_u32x4 d0 = ra_draws(job, c0.x, T);
-                    const rach_u32x4 d1 = ra_draws(job, c1.x, T);
-                    ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i, c0, d0);
-                    ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + nt, c1, d1);
-                    c0 = n0; c1 = n1; i = ni;
+                    const unsigned ni = i + RA_ILP * nt;
+                    uint4 n[RA_ILP];
+                    rach_u32x4 d[RA_ILP];
+#pragma unroll
+                    for (int k = 0; k < RA_ILP; ++k) n[k] = ni + k * nt < nMov ? bT[ni + k * nt] : dead;
+#pragma unroll
+                    for (int k = 0; k < RA_ILP; ++k) d[k] = ra_draws(job, c[k].x, T);
+#pragma unroll
+                    for (int k = 0; k < RA_ILP; ++k) ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * nt, c[k], d[k]);
+#pragma unroll
+                    for (int k = 0; k < RA_ILP; ++k) c[k] = n[k];
+                    i = ni;
                 }
+#else
+                uint4 c0 = i < nMov ? bT[i] : dead;
+                while (i < nMov) {
+                    const unsigned ni = i + nt;
+                    const uint4 n0 = ni < nMov ? bT[ni] : dead;
+                    ra_phase1_mover<DUMP>(job, w, s, acc, T, i, c0);
+                    c0 = n0; i = ni;
+                }
+#endif
                 const unsigned n1 = nMov + (unsigned)s.nArr + s.nM3;
                 for (i = nMov + tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
             }
