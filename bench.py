@@ -246,6 +246,13 @@ def run_our_arm(args):
                              "note": "achieved = updates/s/GPU x 32 B (SURVEY 8d contract); the engine is event-driven and "
                                      "moves fewer bytes than that model, so frac > 1 means avoided traffic -- see "
                                      "`traffic` (ncu dram bytes per launch) and DESIGN.md section 5; peak " + peak_src}}
+        if traffic and args.nue == 100000 and args.reps == 4096 and args.distribution == "beta":
+            # the same kernel against the bytes it REALLY moves (ncu dram__bytes per launch of this workload)
+            real = traffic["dram_bytes_per_launch"] / (kernel_ms / args.steps / 1e3) / 1e9
+            line["roofline_measured_traffic"] = {"bound": "hbm", "achieved": real, "peak": peak, "unit": "GB/s",
+                                                 "frac": real / peak,
+                                                 "note": "ncu dram bytes per launch / CUDA-event kernel time: the kernel is "
+                                                         "issue- and barrier-bound, not DRAM-bound (profiles/r01b_ncu_full_592reps.md)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(args.nue, 1500, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
