@@ -87,6 +87,10 @@ struct RaPointDev {
     unsigned magicBI, magicP, magicA, pad; /* ra_magic() of the three runtime divisors */
     ra_u64 seed;
     const int* arrCum;        /* [nOcc] activeCheck after the arrival step of ms occ*A (W:280-292) */
+    /* byte offsets of the block's tables in dynamic shared memory (ra_layout): a function of (R, P) only, kept
+     * here so that a launch whose replications share one point reads them as kernel constants */
+    unsigned oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore, oExtraFirst, oClsSize;
+    unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes;
 };
 
 /* ---- per-CTA global workspace ------------------------------------------------------------ */
@@ -108,16 +112,6 @@ struct RaWork {
 
 /* ---- per-CTA shared state ---------------------------------------------------------------- */
 struct RaShared {
-    unsigned* cnt;            /* [R*P] cohort size                                          */
-    unsigned* minI;           /* [R*P] lowest UE index of the cohort                         */
-    unsigned* bcount;         /* [R]   records in each move bucket                          */
-    unsigned* m3count;        /* [RA_M3RING]                                                */
-    unsigned *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize;   /* [P] each     */
-    unsigned* hist;           /* [RA_HBINS] singleton scans per index bin (grant selection) */
-    unsigned* sIdx;           /* [RA_SCAP]  first singleton indices of the ms                */
-    uint4*    sLand;          /* [RA_LCAP]  first re-transmitter records of the ms           */
-    unsigned* sLandMeta;      /* [RA_LCAP]                                                   */
-    uint4*    sUnc;           /* [RA_UCAP]  first uncertain movers of the ms                 */
     int grantCheck, activeCheck, acOld, nArr, overflow, nextAc;   /* nextAc: activeCheck after the next arrival step */
     int nextArrMs, occ;       /* next ms with T % A == 0 and its occasion number (no division in the ms loop) */
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
@@ -172,27 +166,86 @@ RA_HD rach_u32x4 ra_draws(const RaJob& job, unsigned ue, int ms) {
     return rach_tape_block(job.pt->seed, job.rep, ue, (unsigned)ms, 0u, RACH_TAPE_TAG_UE);
 }
 
-RA_HD unsigned ra_first_scan(const RaShared& s, unsigned p) {     /* s[p] of the header comment */
-    unsigned a = s.l1[p], b = s.l2[p];
+/* ---- the block's tables in dynamic shared memory ------------------------------------------ */
+/* Tables are addressed as base + pt.o<Table> (32-bit shared addresses: LDS / ATOMS).  Keeping 64-bit table
+ * pointers in shared memory instead made every access a generic LD / ATOM behind a pointer load: 9 % slower at two
+ * replications per block, equal in the long steady state (measured on B200). */
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned char* ra_smem() {
+    extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
+    return ra_dyn_smem;
+}
+#else
+static thread_local unsigned char* ra_emu_smem_base;      /* host emulation of the phases: set by the caller */
+static inline unsigned char* ra_smem() { return ra_emu_smem_base; }
+#endif
+#define RA_TAB_U(off)  (reinterpret_cast<unsigned*>(ra_smem() + (off)))
+#define RA_TAB_Q(off)  (reinterpret_cast<uint4*>(ra_smem() + (off)))
+struct RaTabsT { unsigned *minI, *cnt, *bcount, *m3count, *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize, *hist, *sIdx, *sLandMeta; uint4 *sLand, *sUnc; };
+#define RA_T(name, O) (reinterpret_cast<decltype(RaTabsT::name)>(ra_smem() + pt.O))
+#define S_minI       RA_T(minI, oMinI)             /* [R*P] lowest UE index of the cohort                        */
+#define S_cnt        RA_T(cnt, oCnt)               /* [R*P] cohort size                                          */
+#define S_bcount     RA_T(bcount, oBcount)         /* [R]   records in each move bucket                          */
+#define S_m3count    RA_T(m3count, oM3count)       /* [RA_M3RING]                                                */
+#define S_N          RA_T(N, oN)                   /* [P] each, N .. clsSize                                     */
+#define S_l1         RA_T(l1, oL1)
+#define S_nlList     RA_T(nlList, oNlList)
+#define S_l1m        RA_T(l1m, oL1m)
+#define S_l2         RA_T(l2, oL2)
+#define S_before     RA_T(before, oBefore)
+#define S_extraFirst RA_T(extraFirst, oExtraFirst)
+#define S_clsSize    RA_T(clsSize, oClsSize)
+#define S_hist       RA_T(hist, oHist)             /* [RA_HBINS] singleton scans per index bin (grant selection) */
+#define S_sIdx       RA_T(sIdx, oSIdx)             /* [RA_SCAP]  first singleton indices of the ms                */
+#define S_sLand      RA_T(sLand, oSLand)           /* [RA_LCAP]  first re-transmitter records of the ms           */
+#define S_sLandMeta  RA_T(sLandMeta, oSLandMeta)   /* [RA_LCAP]                                                   */
+#define S_sUnc       RA_T(sUnc, oSUnc)             /* [RA_UCAP]  first uncertain movers of the ms                 */
+
+/* table layout for (R, P); 16-byte records first */
+RA_HD void ra_layout(RaPointDev& pt) {
+    const unsigned RP = (unsigned)pt.R * (unsigned)pt.P, P = (unsigned)pt.P;
+    unsigned o = 0;
+    pt.oSLand = o;      o += 16u * RA_LCAP;
+    pt.oSUnc = o;       o += 16u * RA_UCAP;
+    pt.oSLandMeta = o;  o += 4u * RA_LCAP;
+    pt.oMinI = o;       o += 4u * RP;
+    pt.oCnt = o;        o += 4u * RP;
+    pt.oBcount = o;     o += 4u * (unsigned)pt.R;
+    pt.oM3count = o;    o += 4u * RA_M3RING;
+    pt.oN = o;          o += 4u * P;
+    pt.oL1 = o;         o += 4u * P;
+    pt.oNlList = o;     o += 4u * P;
+    pt.oL1m = o;        o += 4u * P;
+    pt.oL2 = o;         o += 4u * P;
+    pt.oBefore = o;     o += 4u * P;
+    pt.oExtraFirst = o; o += 4u * P;
+    pt.oClsSize = o;    o += 4u * P;
+    pt.oHist = o;       o += 4u * RA_HBINS;
+    pt.oSIdx = o;       o += 4u * RA_SCAP;
+    pt.smemBytes = o;
+}
+
+RA_HD unsigned ra_first_scan(const RaPointDev& pt, unsigned p) {     /* s[p] of the header comment */
+    unsigned a = S_l1[p], b = S_l2[p];
     return a < b ? a : b;
 }
 
 /* per-ms work lists: the first entries live in shared memory (the small phases then never wait for
  * L2), the overflow in the block's global workspace */
 /* (x + 1 <= cap instead of x < cap: no "pointless comparison" diagnostics when a capacity is 0) */
-RA_HD uint4 ra_lrec_get(const RaWork& w, const RaShared& s, unsigned l) { return l + 1 <= RA_LCAP ? s.sLand[l] : w.landerRec[l]; }
-RA_HD unsigned ra_lmeta_get(const RaWork& w, const RaShared& s, unsigned l) { return l + 1 <= RA_LCAP ? s.sLandMeta[l] : w.landerMeta[l]; }
-RA_HD void ra_lmeta_set(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) s.sLandMeta[l] = v; else w.landerMeta[l] = v; }
-RA_HD void ra_lmeta_add(const RaWork& w, RaShared& s, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) RA_AADD(&s.sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
-RA_HD void ra_unc_set(const RaWork& w, RaShared& s, unsigned u, const uint4& e) { if (u + 1 <= RA_UCAP) s.sUnc[u] = e; else w.uncertain[u] = e; }
-RA_HD uint4 ra_unc_get(const RaWork& w, const RaShared& s, unsigned u) { return u + 1 <= RA_UCAP ? s.sUnc[u] : w.uncertain[u]; }
+RA_HD uint4 ra_lrec_get(const RaPointDev& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLand[l] : w.landerRec[l]; }
+RA_HD unsigned ra_lmeta_get(const RaPointDev& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLandMeta[l] : w.landerMeta[l]; }
+RA_HD void ra_lmeta_set(const RaPointDev& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) S_sLandMeta[l] = v; else w.landerMeta[l] = v; }
+RA_HD void ra_lmeta_add(const RaPointDev& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) RA_AADD(&S_sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
+RA_HD void ra_unc_set(const RaPointDev& pt, const RaWork& w, unsigned u, const uint4& e) { if (u + 1 <= RA_UCAP) S_sUnc[u] = e; else w.uncertain[u] = e; }
+RA_HD uint4 ra_unc_get(const RaPointDev& pt, const RaWork& w, unsigned u) { return u + 1 <= RA_UCAP ? S_sUnc[u] : w.uncertain[u]; }
 
 /* append a record to move bucket `m`; returns its position */
 RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
     unsigned slot = (unsigned)m & (unsigned)(pt.R - 1);
     /* one shared-memory atomic per record: measured 8 % faster on B200 than aggregating the lanes of a warp
      * per bucket with __match_any_sync (the variable-mask shuffle that follows costs more than the contention) */
-    unsigned pos = RA_AADD(&s.bcount[slot], 1u);
+    unsigned pos = RA_AADD(&S_bcount[slot], 1u);
     if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
     w.bucket[(size_t)slot * w.cap + pos] = rec;
     return pos;
@@ -204,9 +257,9 @@ RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const
     int m = (int)rec.y + pt.Wn - 1;
     const unsigned pos = ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
-    RA_AADD(&s.cnt[c], 1u);
-    if (rec.x < s.minI[c]) {                              /* plain read first: the minimum rarely moves */
-        if (RA_AMIN(&s.minI[c], rec.x) > rec.x) w.minPos[c] = pos;
+    RA_AADD(&S_cnt[c], 1u);
+    if (rec.x < S_minI[c]) {                              /* plain read first: the minimum rarely moves */
+        if (RA_AMIN(&S_minI[c], rec.x) > rec.x) w.minPos[c] = pos;
     }
 }
 
@@ -218,17 +271,17 @@ RA_HD void ra_park_stale(const RaPointDev& pt, const RaWork& w, RaShared& s, int
     ra_bucket_push(pt, w, s, now + pt.Wn, rec);
 }
 
-RA_HD void ra_msg3_push(const RaWork& w, RaShared& s, int due, const uint4& rec) {
+RA_HD void ra_msg3_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int due, const uint4& rec) {
     unsigned slot = (unsigned)due & (RA_M3RING - 1);
-    unsigned pos = RA_AADD(&s.m3count[slot], 1u);
+    unsigned pos = RA_AADD(&S_m3count[slot], 1u);
     if (pos >= (unsigned)w.cap3) { s.overflow = 1; return; }
     w.msg3[(size_t)slot * w.cap3 + pos] = rec;
 }
 
-RA_HD void ra_lander_push(const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
+RA_HD void ra_lander_push(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
     unsigned l = RA_AADD(&s.nLanders, 1u);
     if (l >= (unsigned)w.cap) { s.overflow = 1; return; }
-    if (l + 1 <= RA_LCAP) { s.sLand[l] = rec; s.sLandMeta[l] = member; }
+    if (l + 1 <= RA_LCAP) { S_sLand[l] = rec; S_sLandMeta[l] = member; }
     else { w.landerRec[l] = rec; w.landerMeta[l] = member; }
 }
 
@@ -256,10 +309,10 @@ RA_HD int ra_sector(int r31) {
 template <bool DUMP>
 RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
     const RaPointDev& pt = *job.pt;
-    for (int i = tid; i < pt.R * pt.P; i += nt) { s.cnt[i] = 0; s.minI[i] = RA_INF32; }
-    for (int i = tid; i < pt.R; i += nt) s.bcount[i] = 0;
-    for (int i = tid; i < RA_M3RING; i += nt) s.m3count[i] = 0;
-    for (int i = tid; i < RA_HBINS; i += nt) s.hist[i] = 0;
+    for (int i = tid; i < pt.R * pt.P; i += nt) { S_cnt[i] = 0; S_minI[i] = RA_INF32; }
+    for (int i = tid; i < pt.R; i += nt) S_bcount[i] = 0;
+    for (int i = tid; i < RA_M3RING; i += nt) S_m3count[i] = 0;
+    for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0;
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
     if (tid == 0) {
         s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0;
@@ -281,12 +334,12 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
         unsigned n = 0, best = RA_INF32, bestm = 0;
         for (int d = 0; d < Wn; ++d) {
             unsigned m = ((unsigned)(T + d) & Rm);
-            n += s.cnt[m * P + p];
-            if (d > 0) { unsigned v = s.minI[m * P + p]; if (v < best) { best = v; bestm = m; } }
+            n += S_cnt[m * P + p];
+            if (d > 0) { unsigned v = S_minI[m * P + p]; if (v < best) { best = v; bestm = m; } }
         }
-        s.N[p] = n;
-        s.l1[p] = best; s.l1m[p] = bestm;
-        s.l2[p] = RA_INF32; s.before[p] = 0; s.extraFirst[p] = 0; s.clsSize[p] = 0;
+        S_N[p] = n;
+        S_l1[p] = best; S_l1m[p] = bestm;
+        S_l2[p] = RA_INF32; S_before[p] = 0; S_extraFirst[p] = 0; S_clsSize[p] = 0;
     }
     if (tid == 0) {
         if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) s.grantCheck = 0;          /* literal 5, W:268 */
@@ -298,8 +351,8 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
             if (s.occ < pt.nOcc) s.nextAc = pt.arrCum[s.occ];                   /* needed A ms from now: latency hidden */
         }
         s.nArr = s.activeCheck - s.acOld;
-        s.nMov = s.bcount[(unsigned)T & Rm];
-        s.nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
+        s.nMov = S_bcount[(unsigned)T & Rm];
+        s.nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
     }
 }
 
@@ -326,7 +379,7 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
     unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
     /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
-    const bool uncertain = !stale && idx < s.l1[p0];
+    const bool uncertain = !stale && idx < S_l1[p0];
     const bool limit = (int)mrc >= pt.M;
     /* both branches draw the backoff: retry W:540 (1st draw), limit W:514 (2nd draw) */
     const int tmp = (int)ra_mod((limit ? d.v[1] : d.v[0]) >> 1, (unsigned)pt.BI, pt.magicBI);
@@ -349,7 +402,7 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
     if (uncertain) {
         unsigned u = RA_AADD(&s.nUnc, 1u);
-        ra_unc_set(w, s, u, make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0));
+        ra_unc_set(pt, w, u, make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0));
         if (limit) {
             if (X == T) { unsigned c = RA_AADD(&s.nC3, 1u); w.c3[c] = make_uint4(idx, p0, pnew, 0); }
             return;
@@ -359,8 +412,8 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     if (X > T) {
         ra_schedule(pt, w, s, nr);                          /* the common case, one call site */
     } else if (X == T) {                                    /* backoff 0 on a tx slot: transmits now */
-        RA_AMIN(&s.l2[pnew], idx);
-        ra_lander_push(w, s, nr, (!stale && !limit) ? 1u : 0u);
+        RA_AMIN(&S_l2[pnew], idx);
+        ra_lander_push(pt, w, s, nr, (!stale && !limit) ? 1u : 0u);
     } else {
         ra_park_stale(pt, w, s, T, nr);                     /* only from an old txTime */
     }
@@ -410,7 +463,7 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
                 }
             } else {                                        /* W:678-679 */
                 rec.y = (unsigned)(T + 48); rec.w |= 0x80000000u;
-                ra_msg3_push(w, s, T + 48, rec);
+                ra_msg3_push(pt, w, s, T + 48, rec);
             }
         } else {
             /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
@@ -436,15 +489,15 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
  * nobody has postponed them: decide in index order (a landing is itself a scan of its new
  * class and postpones the members above it).
  * ========================================================================================= */
-RA_HD void ra_phase2_serial(const RaWork& w, RaShared& s) {
+RA_HD void ra_phase2_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) {
     const unsigned n = s.nC3;
     for (unsigned i = 0; i < n; ++i) {                      /* selection by ascending idx */
         unsigned best = i;
         for (unsigned j = i + 1; j < n; ++j) if (w.c3[j].x < w.c3[best].x) best = j;
         uint4 c = w.c3[best]; w.c3[best] = w.c3[i];
-        if (c.x < ra_first_scan(s, c.y)) {                  /* not postponed: lands on pnew */
+        if (c.x < ra_first_scan(pt, c.y)) {                  /* not postponed: lands on pnew */
             c.w = 1;
-            if (c.x < s.l2[c.z]) s.l2[c.z] = c.x;
+            if (c.x < S_l2[c.z]) S_l2[c.z] = c.x;
         }
         w.c3[i] = c;
     }
@@ -456,10 +509,10 @@ RA_HD void ra_phase2_serial(const RaWork& w, RaShared& s) {
 template <bool DUMP>
 RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned u) {
     const RaPointDev& pt = *job.pt;
-    const uint4 e = ra_unc_get(w, s, u);
+    const uint4 e = ra_unc_get(pt, w, u);
     const unsigned idx = e.y, p0 = e.z & 0xFFu;
-    const unsigned sp = ra_first_scan(s, p0);
-    if (idx < sp) RA_AADD(&s.before[p0], 1u);              /* left the class before its first scan */
+    const unsigned sp = ra_first_scan(pt, p0);
+    if (idx < sp) RA_AADD(&S_before[p0], 1u);              /* left the class before its first scan */
     if (!(e.z >> 31)) return;
     /* limit branch, W:498-531 */
     uint4 rec = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + e.x];
@@ -470,7 +523,7 @@ RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     int X = ra_align(base + tmp, pt.A, pt.magicA);
     uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, ra_rec_fail(rec) + 1), ra_w3(pnew, 0, 1, 0));
     if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;
-    if (X == T) ra_lander_push(w, s, nr, pnew == p0 ? 1u : 0u);   /* s.l2 already holds it (phase 2) */
+    if (X == T) ra_lander_push(pt, w, s, nr, pnew == p0 ? 1u : 0u);   /* S_l2 already holds it (phase 2) */
     else ra_schedule(pt, w, s, nr);                         /* X > T always: base >= T */
 }
 
@@ -478,20 +531,20 @@ RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
  * Phase 3b (only if nE1 > 0) -- a Msg3 restart that landed on T at index k is counted by the
  * first scan of its class at an index above k (W:613-621), which postpones it.
  * ========================================================================================= */
-RA_HD void ra_phase3b_item(const RaWork& w, RaShared& s, unsigned e) {
+RA_HD void ra_phase3b_item(const RaPointDev& pt, const RaWork& w, RaShared& s, unsigned e) {
     const uint4 r = w.e1Rec[e];
     const unsigned k = r.x, q = ra_rec_p(r);
     unsigned bestIdx = RA_INF32, bestRef = RA_INF32;
-    unsigned sq = ra_first_scan(s, q);
-    if (sq != RA_INF32 && sq > k && sq == s.l1[q]) { bestIdx = sq; bestRef = 0x80000000u | q; }
+    unsigned sq = ra_first_scan(pt, q);
+    if (sq != RA_INF32 && sq > k && sq == S_l1[q]) { bestIdx = sq; bestRef = 0x80000000u | q; }
     for (unsigned l = 0; l < s.nLanders; ++l) {
-        const uint4 lr = ra_lrec_get(w, s, l);
+        const uint4 lr = ra_lrec_get(pt, w, l);
         if (ra_rec_p(lr) == q && lr.x > k && lr.x < bestIdx) { bestIdx = lr.x; bestRef = l; }
     }
     if (bestIdx == RA_INF32) return;
     w.e1Meta[e] = 1;
-    if (bestRef & 0x80000000u) RA_AADD(&s.extraFirst[q], 1u);
-    else ra_lmeta_add(w, s, bestRef, 256u);
+    if (bestRef & 0x80000000u) RA_AADD(&S_extraFirst[q], 1u);
+    else ra_lmeta_add(pt, w, bestRef, 256u);
 }
 
 /* =========================================================================================
@@ -501,9 +554,9 @@ RA_HD void ra_phase3b_item(const RaWork& w, RaShared& s, unsigned e) {
  * ========================================================================================= */
 RA_HD void ra_single_push(const RaPointDev& pt, const RaWork& w, RaShared& s, unsigned idx) {
     unsigned k = RA_AADD(&s.nSingles, 1u);
-    if (k < RA_SCAP) s.sIdx[k] = idx;
+    if (k < RA_SCAP) S_sIdx[k] = idx;
     w.singles[k] = idx;
-    RA_AADD(&s.hist[idx >> pt.hshift], 1u);
+    RA_AADD(&S_hist[idx >> pt.hshift], 1u);
 }
 
 RA_HD void ra_count_scan(RaAcc& acc, unsigned size) {
@@ -515,10 +568,10 @@ RA_HD void ra_count_scan(RaAcc& acc, unsigned size) {
 RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
     if (item < (unsigned)pt.P) {
         const unsigned q = item;
-        const unsigned sq = ra_first_scan(s, q);
-        if (sq == RA_INF32 || sq != s.l1[q]) return;        /* no scan, or a lander scans first */
-        unsigned size = s.N[q] - s.before[q] + s.extraFirst[q];
-        s.clsSize[q] = size;
+        const unsigned sq = ra_first_scan(pt, q);
+        if (sq == RA_INF32 || sq != S_l1[q]) return;        /* no scan, or a lander scans first */
+        unsigned size = S_N[q] - S_before[q] + S_extraFirst[q];
+        S_clsSize[q] = size;
         ra_count_scan(acc, size);
         if (size == 1) {
             ra_single_push(pt, w, s, sq);
@@ -527,16 +580,16 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
     }
     const unsigned l = item - (unsigned)pt.P;
     if (l >= s.nLanders) return;
-    const uint4 r = ra_lrec_get(w, s, l);
-    const unsigned q = ra_rec_p(r), meta = ra_lmeta_get(w, s, l);
+    const uint4 r = ra_lrec_get(pt, w, l);
+    const unsigned q = ra_rec_p(r), meta = ra_lmeta_get(pt, w, l);
     unsigned size;
-    if (r.x == ra_first_scan(s, q)) size = s.N[q] - s.before[q] + ((meta & 1u) ? 0u : 1u) + (meta >> 8);
+    if (r.x == ra_first_scan(pt, q)) size = S_N[q] - S_before[q] + ((meta & 1u) ? 0u : 1u) + (meta >> 8);
     else size = 1u + (meta >> 8);
     ra_count_scan(acc, size);
     if (size == 1) {
         ra_single_push(pt, w, s, r.x);
     } else {
-        ra_lmeta_set(w, s, l, meta | 2u);                   /* collided */
+        ra_lmeta_set(pt, w, l, meta | 2u);                   /* collided */
     }
 }
 
@@ -580,7 +633,7 @@ __device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWor
             const unsigned k = (unsigned)K;
             const int per = RA_HBINS / 32;
             unsigned sum = 0;
-            for (int b = 0; b < per; ++b) sum += s.hist[lane * per + b];
+            for (int b = 0; b < per; ++b) sum += S_hist[lane * per + b];
             unsigned incl = sum;
             for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
             const int L = __ffs(__ballot_sync(0xFFFFFFFFu, incl >= k)) - 1;
@@ -588,7 +641,7 @@ __device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWor
             if (lane == L) {
                 unsigned c = incl - sum;
                 for (int b = 0; b < per; ++b) {
-                    unsigned h = s.hist[lane * per + b];
+                    unsigned h = S_hist[lane * per + b];
                     if (c + h >= k) { bstar = (unsigned)(lane * per + b); before = c; break; }
                     c += h;
                 }
@@ -599,7 +652,7 @@ __device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWor
             for (unsigned r = 0; r < kk; ++r) {
                 unsigned best = RA_INF32;
                 for (unsigned j = lane; j < n; j += 32) {
-                    unsigned v = j < RA_SCAP ? s.sIdx[j] : w.singles[j];
+                    unsigned v = j < RA_SCAP ? S_sIdx[j] : w.singles[j];
                     if ((v >> pt.hshift) == bstar && (first || v > prev) && v < best) best = v;
                 }
                 for (int o = 16; o; o >>= 1) { unsigned v = __shfl_xor_sync(0xFFFFFFFFu, best, o); best = v < best ? v : best; }
@@ -620,13 +673,13 @@ RA_HD void ra_grant_nonmover(const RaJob& job, const RaWork& w, RaShared& s, int
     const RaPointDev& pt = *job.pt;
     uint4 rec = w.bucket[at];
     w.bucket[at].x = RA_DEAD;
-    s.cnt[slot * pt.P + q] -= 1; s.minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
+    S_cnt[slot * pt.P + q] -= 1; S_minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
     if (DUMP) {
         int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
         row[8] = T - (int)rec.y + 1; row[9] = (int)ra_rec_mrc(rec);
     }
     rec.y = (unsigned)(T + 11); rec.w &= 0x7FFFFFFFu;
-    ra_msg3_push(w, s, T + 11, rec);
+    ra_msg3_push(pt, w, s, T + 11, rec);
 }
 
 /* =========================================================================================
@@ -639,31 +692,31 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < (unsigned)pt.P) {
         const unsigned q = item;
-        const unsigned sq = ra_first_scan(s, q);
-        if (sq != RA_INF32 && sq == s.l1[q] && s.clsSize[q] == 1 && ra_granted(s, sq)) {
+        const unsigned sq = ra_first_scan(pt, q);
+        if (sq != RA_INF32 && sq == S_l1[q] && S_clsSize[q] == 1 && ra_granted(s, sq)) {
             /* a visible non-mover scanned alone and was granted: active=2, txTime=T+11, W:642-645.  Its record
              * sits in the bucket of its move time, normally at the hinted position */
-            const unsigned slot = s.l1m[q], hint = w.minPos[slot * pt.P + q];
+            const unsigned slot = S_l1m[q], hint = w.minPos[slot * pt.P + q];
             const size_t at = (size_t)slot * w.cap + hint;
 #ifndef RA_NO_POS_HINT
-            if (hint < s.bcount[slot] && w.bucket[at].x == sq) ra_grant_nonmover<DUMP>(job, w, s, T, q, slot, at);
+            if (hint < S_bcount[slot] && w.bucket[at].x == sq) ra_grant_nonmover<DUMP>(job, w, s, T, q, slot, at);
             else
 #endif
-            { unsigned k = RA_AADD(&s.nNl, 1u); s.nlList[k] = q; }      /* rare: found by ra_phase6b */
+            { unsigned k = RA_AADD(&s.nNl, 1u); S_nlList[k] = q; }      /* rare: found by ra_phase6b */
         }
-        if (q == 0) { s.bcount[(unsigned)T & Rm] = 0; s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
+        if (q == 0) { S_bcount[(unsigned)T & Rm] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
         /* the cohort that moved in this ms is gone */
-        s.cnt[((unsigned)T & Rm) * pt.P + q] = 0; s.minI[((unsigned)T & Rm) * pt.P + q] = RA_INF32;
+        S_cnt[((unsigned)T & Rm) * pt.P + q] = 0; S_minI[((unsigned)T & Rm) * pt.P + q] = RA_INF32;
         return;
     }
     item -= (unsigned)pt.P;
     if (item < s.nLanders) {
-        uint4 r = ra_lrec_get(w, s, item);
-        const unsigned meta = ra_lmeta_get(w, s, item);
+        uint4 r = ra_lrec_get(pt, w, item);
+        const unsigned meta = ra_lmeta_get(pt, w, item);
         if (!(meta & 2u) && ra_granted(s, r.x)) {
             if (DUMP) { int* row = job.dump + (size_t)r.x * RA_DUMP_W; row[8] = 0; row[9] = (int)ra_rec_mrc(r); }
             r.y = (unsigned)(T + 11);
-            ra_msg3_push(w, s, T + 11, r);
+            ra_msg3_push(pt, w, s, T + 11, r);
         } else {
             r.y = (unsigned)(T + 1);                        /* txTime++, W:647 / W:658 */
             ra_schedule(pt, w, s, r);                       /* rarWindow 0 now -> expires at T+Wn */
@@ -683,9 +736,10 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
  * time by index. */
 template <bool DUMP>
 RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
+    const RaPointDev& pt = *job.pt;
     for (unsigned e = 0; e < s.nNl; ++e) {
-        const unsigned q = s.nlList[e], slot = s.l1m[q], want = s.l1[q];
-        const unsigned n = s.bcount[slot];
+        const unsigned q = S_nlList[e], slot = S_l1m[q], want = S_l1[q];
+        const unsigned n = S_bcount[slot];
         for (unsigned j = tid; j < n; j += nt) {
             const size_t at = (size_t)slot * w.cap + j;
             if (w.bucket[at].x != want) continue;
@@ -697,8 +751,8 @@ RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int
 /* with phase 6 (every thread), only if the ms had singleton scans */
 RA_HD void ra_hist_clear(const RaPointDev& pt, const RaWork& w, RaShared& s, int tid, int nt) {
     const unsigned n = s.nSingles;
-    if (n > RA_HBINS / 2) { for (int i = tid; i < RA_HBINS; i += nt) s.hist[i] = 0; }
-    else for (unsigned j = tid; j < n; j += nt) s.hist[(j < RA_SCAP ? s.sIdx[j] : w.singles[j]) >> pt.hshift] = 0;
+    if (n > RA_HBINS / 2) { for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0; }
+    else for (unsigned j = tid; j < n; j += nt) S_hist[(j < RA_SCAP ? S_sIdx[j] : w.singles[j]) >> pt.hshift] = 0;
 }
 
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */
@@ -717,7 +771,7 @@ RA_HD void ra_dump_inflight(const RaJob& job, const RaWork& w, RaShared& s, int 
     for (int slot = 0; slot < pt.R; ++slot) {
         /* absolute move time of this slot: the value in (last, last+R] congruent to slot */
         int m = last + 1 + (int)(((unsigned)slot - (unsigned)(last + 1)) & (unsigned)(pt.R - 1));
-        for (unsigned j = tid; j < s.bcount[slot]; j += nt) {
+        for (unsigned j = tid; j < S_bcount[slot]; j += nt) {
             uint4 r = w.bucket[(size_t)slot * w.cap + j];
             if (r.x == RA_DEAD) continue;
             int* row = job.dump + (size_t)r.x * RA_DUMP_W;
@@ -738,7 +792,7 @@ RA_HD void ra_dump_inflight(const RaJob& job, const RaWork& w, RaShared& s, int 
         }
     }
     for (int slot = 0; slot < RA_M3RING; ++slot) {
-        for (unsigned j = tid; j < s.m3count[slot]; j += nt) {
+        for (unsigned j = tid; j < S_m3count[slot]; j += nt) {
             uint4 r = w.msg3[(size_t)slot * w.cap3 + j];
             int* row = job.dump + (size_t)r.x * RA_DUMP_W;
             row[0] = last + 1 - (int)ra_rec_ts(r);

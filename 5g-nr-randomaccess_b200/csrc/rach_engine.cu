@@ -28,12 +28,22 @@
 #include "rach_gpu.h"
 #include "rach_host.h"
 
+/* Block shapes of the W step kernel (threads, resident blocks per SM the register budget is sized for).
+ * Measured on B200, 4096 replications x 100k UEs: 128 x 8 (64 registers, no spills) 1215 ms, 256 x 5 (48 registers)
+ * 1259 ms, 192 x 6 1241 ms, 96 x 10 1286 ms, 64 x 11 1337 ms, 512 x 2 1515 ms -- the block-wide barriers between
+ * the phases cost less with 4 warps than with 8.  The small shape needs 8 blocks' tables in one SM's shared
+ * memory; points with a large ring x preamble product fall back to 256 x 5 (fewer, larger blocks). */
 #ifndef RA_NT
-#define RA_NT 256          /* threads per block */
+#define RA_NT 128          /* small shape */
 #endif
 #ifndef RA_MINB
-#define RA_MINB (1280 / RA_NT) /* resident blocks per SM the register budget is sized for: 5 x 256 threads at 48
-                                 registers measured 3.8 % faster than 4 x 64 on the 4096-replication workload, 6 x 40 slower */
+#define RA_MINB 8
+#endif
+#define RA_NT_BIG 256
+#define RA_MINB_BIG 5
+#ifndef RA_NT_N
+#define RA_NT_N 192        /* variant N: phase B runs one warp leader per sector, 6 warps = 6 sectors.  Measured */
+#define RA_MINB_N 5        /* (50k UEs x 2048 replications): 192 x 5 169 ms, 128 x 8 174 ms, 256 x 4 203 ms    */
 #endif
 #define RA_NPHASE 10
 #ifndef RA_ILP
@@ -61,29 +71,8 @@ struct RaKernelArgs {
     int               nJobs, maxP, maxR;
 };
 
-__device__ __forceinline__ void ra_carve(RaShared& s, unsigned char* base, int R, int P) {
-    s.sLand = reinterpret_cast<uint4*>(base);                  base += sizeof(uint4) * RA_LCAP;
-    s.sUnc = reinterpret_cast<uint4*>(base);                   base += sizeof(uint4) * RA_UCAP;
-    s.sLandMeta = reinterpret_cast<unsigned*>(base);           base += sizeof(unsigned) * RA_LCAP;
-    s.minI = reinterpret_cast<unsigned*>(base);                base += sizeof(unsigned) * (size_t)R * P;
-    s.cnt = reinterpret_cast<unsigned*>(base);                 base += sizeof(unsigned) * (size_t)R * P;
-    s.bcount = reinterpret_cast<unsigned*>(base);              base += sizeof(unsigned) * (size_t)R;
-    s.m3count = reinterpret_cast<unsigned*>(base);             base += sizeof(unsigned) * RA_M3RING;
-    unsigned* c = reinterpret_cast<unsigned*>(base);
-    s.N = c; s.l1 = c + P; s.nlList = c + 2 * P; s.l1m = c + 3 * P; s.l2 = c + 4 * P;
-    s.before = c + 5 * P; s.extraFirst = c + 6 * P; s.clsSize = c + 7 * P;
-    s.hist = c + 8 * P; s.sIdx = s.hist + RA_HBINS;
-}
-
-static size_t ra_smem_bytes(int R, int P) {
-    return sizeof(uint4) * (RA_LCAP + RA_UCAP) + sizeof(unsigned) * RA_LCAP +
-           2 * sizeof(unsigned) * (size_t)R * P + sizeof(unsigned) * (size_t)R +
-           sizeof(unsigned) * RA_M3RING + sizeof(unsigned) * 8 * (size_t)P + sizeof(unsigned) * (RA_HBINS + RA_SCAP);
-}
-
-template <bool DUMP>
-__global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a) {
-    extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
+template <bool DUMP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
     __shared__ RaShared s;
     __shared__ RaPointDev sPt;
     __shared__ int sJob;
@@ -100,12 +89,11 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
         __syncthreads();
         const int jobId = sJob;
         if (jobId >= a.nJobs) break;
-        if (tid == 0) {
-            sPt = a.points[a.jobPoint[jobId]];
-            ra_carve(s, ra_dyn_smem, sPt.R, sPt.P);
-        }
+        if (tid == 0) sPt = a.points[a.jobPoint[jobId]];
         __syncthreads();
-        const RaPointDev& pt = sPt;         /* (a thread-local copy was measured: spills, 3 % slower) */
+        /* (a thread-local copy of the point was measured: spills, 3 % slower; the point as a kernel constant, for
+         * launches with one point: constant-bank loads in divergent code, 4-7 % slower than these shared loads) */
+        const RaPointDev& pt = sPt;
         RaJob job; job.pt = &pt; job.rep = a.jobRep[jobId];
         job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
         ra_job_init<DUMP>(job, s, tid, nt);
@@ -158,7 +146,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
             __syncthreads();
             RA_TICK(1);
             if (s.nC3) {
-                if (tid == 0) ra_phase2_serial(w, s);
+                if (tid == 0) ra_phase2_serial(pt, w, s);
                 __syncthreads();
                 RA_TICK(2);
             }
@@ -170,7 +158,7 @@ __global__ void __launch_bounds__(RA_NT, RA_MINB) ra_step_kernel(RaKernelArgs a)
             }
             if (s.nE1) {
                 const unsigned n = s.nE1;
-                for (unsigned i = tid; i < n; i += nt) ra_phase3b_item(w, s, i);
+                for (unsigned i = tid; i < n; i += nt) ra_phase3b_item(pt, w, s, i);
                 __syncthreads();
                 RA_TICK(4);
             }
@@ -244,7 +232,7 @@ static size_t rn_smem_bytes(int R, int P) {
 }
 
 template <bool DUMP>
-__global__ void __launch_bounds__(RA_NT, 4) ra_step_kernel_n(RaKernelArgs a) {     /* fp64 activation math: 64 registers, no spills */
+__global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelArgs a) {     /* fp64 activation math: 64 registers, no spills */
     extern __shared__ __align__(16) unsigned char ra_dyn_smem[];
     __shared__ RaSharedN s;
     __shared__ RaPointDev sPt;
@@ -275,7 +263,8 @@ __global__ void __launch_bounds__(RA_NT, 4) ra_step_kernel_n(RaKernelArgs a) {  
                 const unsigned nTx = s.bcount[(unsigned)T & Rm];
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
                 __syncthreads();
-                if ((tid & 31) == 0 && (tid >> 5) < (pt.geometry ? RA_NSECT : 1)) rn_phaseB_sector(job, w, s, T, tid >> 5);
+                if ((tid & 31) == 0)
+                    for (int sec = tid >> 5; sec < (pt.geometry ? RA_NSECT : 1); sec += nt >> 5) rn_phaseB_sector(job, w, s, T, sec);
                 __syncthreads();
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseC_item<DUMP>(job, w, s, T, j);
                 __syncthreads();
@@ -378,10 +367,15 @@ struct RaDev {
     ra_stats* dStats = nullptr; RaWork* dWorks = nullptr; RaWorkN* dWorksN = nullptr; unsigned char* dWorkspace = nullptr;
     double* dGainDump = nullptr;
     int* dDump = nullptr; int* dErr = nullptr; float* dGeom = nullptr; ra_u64* dCyc = nullptr;
-    int grid = 0; size_t smem = 0;
+    int grid = 0, nt = 0; size_t smem = 0; const void* kern = nullptr;
     cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<ra_stats> hStats;
 };
+
+static const void* ra_step_entry(bool dump, bool big) {
+    if (dump) return big ? (const void*)ra_step_kernel<true, RA_NT_BIG, RA_MINB_BIG> : (const void*)ra_step_kernel<true, RA_NT, RA_MINB>;
+    return big ? (const void*)ra_step_kernel<false, RA_NT_BIG, RA_MINB_BIG> : (const void*)ra_step_kernel<false, RA_NT, RA_MINB>;
+}
 
 struct ra_sim {
     std::vector<ra_params> points;
@@ -398,6 +392,7 @@ struct ra_sim {
     int maxP = 0, maxR = 0, cap = 0, cap3 = 0, variant = RA_VARIANT_W;
     std::string err;
 };
+
 
 static thread_local std::string g_createErr;
 
@@ -476,21 +471,30 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     /* grid and per-block workspace */
     const bool isN = sim->variant == RA_VARIANT_N;
     const bool dump = sim->opt.dumpUEs != 0;
-    d.smem = isN ? rn_smem_bytes(sim->maxR, sim->maxP) : ra_smem_bytes(sim->maxR, sim->maxP);
+    d.smem = 0;
+    if (isN) d.smem = rn_smem_bytes(sim->maxR, sim->maxP);
+    else for (const RaPointDev& hp : sim->hostPoints) d.smem = std::max(d.smem, (size_t)hp.smemBytes);
     if (d.smem > (size_t)prop.sharedMemPerBlockOptin) {
         sim->err = "per-replication tables (ring x preambles) exceed the shared memory of one block"; return RA_E_INVAL;
     }
+    /* W: the small block shape if RA_MINB blocks' tables (+1 KB reserved per block) fit in one SM, else the big one
+     * (RACH_BLOCK=big|small overrides, for tuning) */
+    bool big = (d.smem + 1024) * RA_MINB > (size_t)prop.sharedMemPerMultiprocessor;
+    if (const char* bs = getenv("RACH_BLOCK")) big = bs[0] == 'b';
+    d.nt = isN ? RA_NT_N : (big ? RA_NT_BIG : RA_NT);
+    const int minb = isN ? RA_MINB_N : (big ? RA_MINB_BIG : RA_MINB);
     const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
-                           : (dump ? (const void*)ra_step_kernel<true> : (const void*)ra_step_kernel<false>);
+                           : ra_step_entry(dump, big);
+    d.kern = kern;
     RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
     /* the driver's default carveout heuristic was the best of {default, 50, 60, 75, 100 %} (within 0.6 %);
      * RACH_CARVEOUT=<percent> overrides it for tuning */
     if (const char* cv = getenv("RACH_CARVEOUT"))
         RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
     int occ = 0;
-    RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RA_NT, d.smem));
+    RA_CUDA(sim, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, d.nt, d.smem));
     if (occ < 1) { sim->err = "step kernel does not fit on an SM"; return RA_E_INVAL; }
-    int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, RA_MINB);
+    int perSM = sim->opt.ctasPerSM > 0 ? std::min(sim->opt.ctasPerSM, occ) : std::min(occ, minb);
     if (isN && dump) {
         cudaError_t e = cudaMalloc(&d.dGainDump, sizeof(double) * (size_t)sim->cap * (size_t)std::max(nJobs, 1));
         if (e != cudaSuccess) { sim->err = "gain dump buffer does not fit on the device"; return RA_E_NOMEM; }
@@ -631,7 +635,7 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
         RA_CUDA(sim, cudaMemsetAsync(d.dErr, 0, sizeof(int), d.stream));
         RA_CUDA(sim, cudaMemsetAsync(d.dCyc, 0, sizeof(ra_u64) * RA_NPHASE, d.stream));
-        RaKernelArgs a;
+        RaKernelArgs a; memset(&a, 0, sizeof a);
         a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
         a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = sim->opt.phaseTimers ? d.dCyc : nullptr;
         a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
@@ -642,11 +646,10 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         if (sim->variant == RA_VARIANT_U0) {
             if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, RA_U0_NT, 0, d.stream>>>(a, sim->cap);
             else ra_u0_kernel<false><<<d.grid, RA_U0_NT, 0, d.stream>>>(a, sim->cap);
-        } else if (sim->variant == RA_VARIANT_N) {
-            if (sim->opt.dumpUEs) ra_step_kernel_n<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
-            else ra_step_kernel_n<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
-        } else if (sim->opt.dumpUEs) ra_step_kernel<true><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
-        else ra_step_kernel<false><<<d.grid, RA_NT, d.smem, d.stream>>>(a);
+        } else {
+            void* kargs[] = {&a};
+            RA_CUDA(sim, cudaLaunchKernel(d.kern, dim3(d.grid), dim3(d.nt), kargs, d.smem, d.stream));
+        }
         RA_CUDA(sim, cudaGetLastError());
         RA_CUDA(sim, cudaEventRecord(d.e1, d.stream));
         RA_CUDA(sim, cudaMemcpyAsync(d.hStats.data(), d.dStats, sizeof(ra_stats) * nJobs, cudaMemcpyDeviceToHost, d.stream));

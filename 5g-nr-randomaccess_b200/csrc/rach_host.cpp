@@ -149,6 +149,7 @@ void ra_host_fill_point(RaPointDev* pt) {
     int sh = 0;
     while (((pt->nUE - 1) >> sh) >= RA_HBINS) ++sh;
     pt->hshift = sh;
+    ra_layout(*pt);
 }
 
 /* variant U0: RaPointDev.G carries nAccessUE = ceil(n*5/60000), at least 1 (U0:60-64) */

@@ -52,14 +52,10 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     w.singles = singles.data(); w.e1Rec = e1Rec.data(); w.e1Meta = e1Meta.data();
 
     RaShared s; memset(&s, 0, sizeof s);
-    std::vector<unsigned> cnt((size_t)pt.R * pt.P), bcount(pt.R), m3count(RA_M3RING), cls((size_t)pt.P * 8), hist(RA_HBINS), sIdx(RA_SCAP);
-    std::vector<unsigned> minI((size_t)pt.R * pt.P), minPos((size_t)pt.R * pt.P);
-    s.cnt = cnt.data(); s.minI = minI.data(); w.minPos = minPos.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
-    s.N = cls.data(); s.l1 = s.N + pt.P; s.nlList = s.l1 + pt.P; s.l1m = s.nlList + pt.P; s.l2 = s.l1m + pt.P;
-    s.hist = hist.data(); s.sIdx = sIdx.data();
-    std::vector<uint4> sLand(RA_LCAP), sUnc(RA_UCAP); std::vector<unsigned> sLandMeta(RA_LCAP);
-    s.sLand = sLand.data(); s.sUnc = sUnc.data(); s.sLandMeta = sLandMeta.data();
-    s.before = s.l2 + pt.P; s.extraFirst = s.before + pt.P; s.clsSize = s.extraFirst + pt.P;
+    std::vector<unsigned> minPos((size_t)pt.R * pt.P);
+    w.minPos = minPos.data();
+    std::vector<uint4> smem((pt.smemBytes + 15) / 16 + 1);         /* the block's dynamic shared memory (ra_layout) */
+    ra_emu_smem_base = reinterpret_cast<unsigned char*>(smem.data());
 
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
     std::vector<RaAcc> acc(NT); memset(acc.data(), 0, sizeof(RaAcc) * NT);
@@ -70,9 +66,9 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
         for (int t = 0; t < NT; ++t) ra_phase0(job, s, T, t, NT);
         unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
-        if (s.nC3) ra_phase2_serial(w, s);
+        if (s.nC3) ra_phase2_serial(pt, w, s);
         if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
-        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(w, s, i); }
+        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
         unsigned n4 = (unsigned)pt.P + s.nLanders;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
         if (s.nSingles) ra_phase5_serial(pt, w, s);
