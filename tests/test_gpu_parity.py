@@ -96,6 +96,30 @@ def test_fuzz_against_oracle(pkg, oracle):
         np.testing.assert_array_equal(ue, ue_ref, err_msg=str(kw))
 
 
+def test_both_block_shapes(pkg, oracle, monkeypatch):
+    """The W step kernel has two instantiations (128 x 8 and 256 x 5 threads x blocks/SM, picked by table size);
+    RACH_BLOCK forces one.  Both must reproduce the oracle, with and without the per-UE dump."""
+    cases = [dict(nUE=6000, seed=11, rep=3), dict(nUE=2500, nPreamble=64, backoffIndicator=40, nGrantUL=4, seed=12),
+             dict(nUE=3000, distribution=1, nPreamble=3, maxRarWindow=9, accessTime=7, seed=13, geometry=1)]
+    for kw in cases:
+        res, ue_ref, _ = oracle.run_port(oracle.make_config(**kw))
+        for shape in ("big", "small"):
+            monkeypatch.setenv("RACH_BLOCK", shape)
+            st, ue, _ = _run_gpu(pkg, kw)
+            st2, _, _ = _run_gpu(pkg, kw, dump=False)
+            for k in KEYS:
+                assert getattr(st, k) == getattr(res, k) == getattr(st2, k), (k, shape, kw)
+            np.testing.assert_array_equal(ue, ue_ref, err_msg="%s %s" % (shape, kw))
+    monkeypatch.delenv("RACH_BLOCK")
+    # a point whose tables do not fit 8 times in one SM takes the big shape by itself
+    kw = dict(nUE=4000, nPreamble=64, backoffIndicator=100, seed=14)
+    res, ue_ref, _ = oracle.run_port(oracle.make_config(**kw))
+    st, ue, _ = _run_gpu(pkg, kw)
+    for k in KEYS:
+        assert getattr(st, k) == getattr(res, k), (k, kw)
+    np.testing.assert_array_equal(ue, ue_ref)
+
+
 def test_against_reference_sources_in_tape_mode(pkg, oracle):
     if not oracle.ref_available("w"):
         pytest.skip("oracle/_ref not shipped")
