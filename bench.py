@@ -252,7 +252,7 @@ def run_our_arm(args):
             line["roofline_measured_traffic"] = {"bound": "hbm", "achieved": real, "peak": peak, "unit": "GB/s",
                                                  "frac": real / peak,
                                                  "note": "ncu dram bytes per launch / CUDA-event kernel time: the kernel is "
-                                                         "issue- and barrier-bound, not DRAM-bound (profiles/r01b_ncu_full_592reps.md)"}
+                                                         "latency-bound at a balanced pipe mix, not DRAM-bound (profiles/r01d_ncu_128x8.md)"}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_sample(args.nue, 1500, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
