@@ -10,7 +10,9 @@
  * ONE THREAD PER REPLICATION walks the ms loop over a compact, index-ordered list of the live
  * UEs (arrived, not finished; dropped UEs stay as "phantoms") and performs the reference's own
  * steps on it -- the O(nUE) loops of the reference shrink to O(live).  Replications are
- * independent, so a launch runs thousands of them side by side.  Not tuned (secondary variant).
+ * independent, so a launch runs thousands of them side by side, each in a warp of its own (the walks
+ * diverge completely), the head of the live list in shared memory.  A lane-parallel formulation like W's
+ * is the next step for this variant.
  */
 #ifndef RACH_CORE_U0_CUH
 #define RACH_CORE_U0_CUH
@@ -45,8 +47,11 @@ RA_HD void ru_dump_row(int* o, const RuUE& u) {
  * predicate of U0:207 in the one ms where txTime+2 == time; a group update then moves them to time+3
  * (U0:228-229) so they can match again 5 ms later.  They are kept out of the live list in `ph[]`,
  * chained per ms of their next possible match (pad0 = next node, -1 ends the chain). */
+/* The first `winCap` entries of the live list live in `win` (shared memory on the device: the live set is a few dozen
+ * UEs, and a thread that walks it every ms out of L2 spends its time waiting), the rest in `live` (global). */
+#define RU_L(x) (*((x) < winCap ? win + (x) : live + (x)))
 template <bool DUMP>
-RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHead, int cap, RuStats* out) {
+RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* win, int winCap, RuUE* ph, int* phHead, int cap, RuStats* out) {
     const RaPointDev& pt = *job.pt;
     const int nUE = pt.nUE, P = pt.P, BI = pt.BI, maxTime = pt.maxTime, accessTime = 5;   /* U0:57,59 */
     const int nAccessUE = pt.G;                       /* host: ceil(n*5/60000), at least 1 (U0:60-64) */
@@ -70,12 +75,12 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter = 0; u.msg2Flag = 0;
                 u.connectionRequest = 0; u.msg4Flag = 0; u.preambleChange = 0; u.raFailed = 0; u.nowBackoff = 0;
                 u.pad0 = u.pad1 = 0;
-                live[nLive++] = u;
+                RU_L(nLive) = u; ++nLive;
             }
         }
         const int slot = time & ringMask;
         for (int a = 0; a < nLive; ++a) {
-            RuUE u = live[a];
+            RuUE u = RU_L(a);
             if (u.active == -2) continue;                                     /* finished or moved to ph[] */
             unsigned k = 0;
             if (u.active == 1 && u.msg2Flag == 0) {                           /* selectPreamble U0:157-197 */
@@ -96,10 +101,10 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 }
             }
             if (u.txTime + 2 == time && u.txTime != -1) {                     /* preambleCollision U0:107-110, 200-233 */
-                live[a] = u;                                                  /* the scan below reads the list */
+                RU_L(a) = u;                                                  /* the scan below reads the list */
                 int check = 0;
                 for (int b = 0; b < nLive; ++b)
-                    if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) check++;
+                    { const RuUE& o = RU_L(b); if (o.active == 1 && o.txTime + 2 == time && o.preamble == u.preamble) check++; }
                 for (int n = phHead[slot]; n >= 0; n = ph[n].pad0)
                     if (ph[n].txTime + 2 == time && ph[n].preamble == u.preamble) check++;
                 if (check == 1) {
@@ -108,9 +113,10 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 } else {
                     st.collisionPreambles += check;
                     for (int b = 0; b < nLive; ++b)
-                        if (live[b].active == 1 && live[b].txTime + 2 == time && live[b].preamble == u.preamble) {
-                            live[b].rarWindow = 5; live[b].txTime = time + 3;
-                        }
+                    {
+                        RuUE& o = RU_L(b);
+                        if (o.active == 1 && o.txTime + 2 == time && o.preamble == u.preamble) { o.rarWindow = 5; o.txTime = time + 3; }
+                    }
                     /* phantoms of this class: same update, then they can match again at time+5 */
                     int prev = -1;
                     for (int n = phHead[slot]; n >= 0;) {
@@ -122,7 +128,7 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                         } else prev = n;
                         n = next;
                     }
-                    u = live[a];                                              /* the scanner may be a member */
+                    u = RU_L(a);                                              /* the scanner may be a member */
                 }
             }
             if (u.active == 2 && u.txTime + 2 == time) {                      /* requestResourceAllocation U0:113-115, 235-257 */
@@ -154,22 +160,24 @@ RA_HD void ru_run_replication(const RaJob& job, RuUE* live, RuUE* ph, int* phHea
                 }
                 nGone++; u.active = -2;
             }
-            live[a] = u;
+            RU_L(a) = u;
         }
         phHead[slot] = -1;                                                    /* whoever was not hit never matches again */
         if (st.nSuccess == nUE) break;                                        /* U0:122-125 */
         if (nGone > 16 && nGone * 4 > nLive) {                                /* compact, keeping index order */
             int w = 0;
-            for (int a = 0; a < nLive; ++a) if (live[a].active != -2) { if (w != a) live[w] = live[a]; ++w; }
+            for (int a = 0; a < nLive; ++a) if (RU_L(a).active != -2) { if (w != a) RU_L(w) = RU_L(a); ++w; }
             nLive = w; nGone = 0;
         }
     }
     st.simTime = time;
     if (DUMP) {
-        for (int a = 0; a < nLive; ++a) if (live[a].active != -2) ru_dump_row(job.dump + (size_t)live[a].idx * RA_DUMP_W, live[a]);
+        for (int a = 0; a < nLive; ++a) if (RU_L(a).active != -2) ru_dump_row(job.dump + (size_t)RU_L(a).idx * RA_DUMP_W, RU_L(a));
         for (int n = 0; n < nPh; ++n) ru_dump_row(job.dump + (size_t)ph[n].idx * RA_DUMP_W, ph[n]);
     }
     *out = st;
 }
+
+#undef RU_L
 
 #endif /* RACH_CORE_U0_CUH */

@@ -199,8 +199,9 @@ extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, fl
     std::vector<int> phHead((size_t)pt.R);
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = perUE;
     RuStats st;
-    if (perUE) ru_run_replication<true>(job, live.data(), ph.data(), phHead.data(), pt.nUE, &st);
-    else ru_run_replication<false>(job, live.data(), ph.data(), phHead.data(), pt.nUE, &st);
+    std::vector<RuUE> win(5);                      /* a 5-entry window: both halves of the split live list are exercised */
+    if (perUE) ru_run_replication<true>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, &st);
+    else ru_run_replication<false>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, &st);
     memset(res, 0, sizeof *res);
     res->simTimeMs = st.simTime; res->nSuccess = st.nSuccess; res->preambleTxSum = st.txSum; res->delaySum = st.delaySum;
     res->collisionPreambles = st.collisionPreambles; res->totalPreambleTxop = st.totalPreambleTxop;
