@@ -49,12 +49,6 @@
 #ifndef RA_ILP
 #define RA_ILP 2             /* movers per thread and loop iteration (interleaved Philox chains) */
 #endif
-#ifndef RA_U0_NT
-#define RA_U0_NT 1           /* variant U0: replications per block.  One: each replication is a data-dependent walk with
-                                its own control flow, and replications that share a warp serialise each other's
-                                branches (measured, 100k UEs x 1024 replications: 8 per block 2680 ms, 2 1243 ms, 1 848 ms;
-                                throughput at 16k replications 3070/s against 1530/s) */
-#endif
 #define RA_TICK(k) do { if (timers && tid == 0) { long long now_ = clock64(); sCyc[k] += (ra_u64)(now_ - tick); tick = now_; } } while (0)
 
 struct RaKernelArgs {
@@ -305,33 +299,39 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
 }
 
 /* ------------------------------------------------------------------------------------------
- * Variant U0 (RandomAccessSimulator.c): one thread per replication, in a warp of its own (rach_core_u0.cuh).
+ * Variant U0 (RandomAccessSimulator.c): one warp per replication, one lane per live UE (rach_core_u0.cuh).
+ * Measured on the way here (100k UEs x 1024 replications): one thread per replication, 8 replications per warp 2680 ms
+ * (the walks serialise each other's branches), one per warp 848 ms.
  * ------------------------------------------------------------------------------------------ */
-#define RU_WIN 64            /* live-list entries per replication kept in shared memory */
-#define RU_WIN_STRIDE (RU_WIN * sizeof(RuUE) + 16)      /* +16 B: the threads of a block (if several) hit different banks */
+#define RU_WIN 64            /* live-list entries per replication kept in shared memory (the warp step needs >= 32) */
 static size_t ru_smem_bytes(int maxR, bool headsInSmem) {
-    return RA_U0_NT * RU_WIN_STRIDE + (headsInSmem ? (size_t)RA_U0_NT * maxR * sizeof(int) : 0);
+    return RU_WIN * sizeof(RuUE) + (headsInSmem ? (size_t)maxR * sizeof(int) : 0);
 }
 
+/* one warp (= one block) per replication; lanesOn = 0 runs the serial step on lane 0 in every ms */
 template <bool DUMP>
-__global__ void __launch_bounds__(RA_U0_NT) ra_u0_kernel(RaKernelArgs a, int cap, int headsInSmem) {
+__global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap, int headsInSmem, int lanesOn) {
     extern __shared__ __align__(16) unsigned char ru_dyn_smem[];
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    /* per thread: live list [cap], phantom store [cap], phantom calendar heads [maxR ints] */
-    const size_t perThread = 2 * (size_t)cap + ((size_t)a.maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE);
-    RuUE* live = a.liveBase + (size_t)gtid * perThread;
+    const int lane = threadIdx.x;
+    /* per block: live-list overflow [cap], phantom store [cap], phantom calendar heads [maxR ints] */
+    const size_t perBlock = 2 * (size_t)cap + ((size_t)a.maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE);
+    RuUE* live = a.liveBase + (size_t)blockIdx.x * perBlock;
     RuUE* ph = live + cap;
     int* phHead = reinterpret_cast<int*>(ph + cap);
-    RuUE* win = reinterpret_cast<RuUE*>(ru_dyn_smem + threadIdx.x * RU_WIN_STRIDE);
-    if (headsInSmem) phHead = reinterpret_cast<int*>(ru_dyn_smem + RA_U0_NT * RU_WIN_STRIDE) + threadIdx.x * a.maxR;
+    RuUE* win = reinterpret_cast<RuUE*>(ru_dyn_smem);
+    if (headsInSmem) phHead = reinterpret_cast<int*>(ru_dyn_smem + RU_WIN * sizeof(RuUE));
     for (;;) {
-        const int jobId = (int)atomicAdd(a.jobCounter, 1u);
+        int jobId = 0;
+        if (lane == 0) jobId = (int)atomicAdd(a.jobCounter, 1u);
+        jobId = __shfl_sync(0xFFFFFFFFu, jobId, 0);
         if (jobId >= a.nJobs) break;
         const RaPointDev* pt = &a.points[a.jobPoint[jobId]];
         RaJob job; job.pt = pt; job.rep = a.jobRep[jobId];
         job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
         RuStats st;
-        ru_run_replication<DUMP>(job, live, win, RU_WIN, ph, phHead, cap, &st);
+        ru_run_replication<DUMP>(job, live, win, RU_WIN, ph, phHead, cap, lanesOn, &st);
+        __syncwarp();
+        if (lane != 0) continue;
         ra_stats o; memset(&o, 0, sizeof o);
         o.simTimeMs = st.simTime; o.nSuccess = st.nSuccess; o.preambleTxSum = st.txSum; o.delaySum = st.delaySum;
         o.continueFailed = st.dropped; o.finalSuccess = st.nSuccess;
@@ -469,16 +469,16 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     }
 
     if (sim->variant == RA_VARIANT_U0) {
-        /* one thread per replication; global live list + phantom store of cap UEs (64 B each) per thread */
+        /* one warp (block) per replication; global live-list overflow + phantom store of cap UEs (64 B each) per block */
         size_t freeB = 0, totalB = 0;
         RA_CUDA(sim, cudaMemGetInfo(&freeB, &totalB));
         const size_t perThread = sizeof(RuUE) * (2 * (size_t)sim->cap + ((size_t)sim->maxR * sizeof(int) + sizeof(RuUE) - 1) / sizeof(RuUE));
         long long threads = std::min<long long>(nJobs, (long long)((double)freeB * 0.85 / (double)perThread));
-        threads = std::min<long long>(threads, (long long)prop.multiProcessorCount * 32 * RA_U0_NT);   /* resident blocks */
+        threads = std::min<long long>(threads, (long long)prop.multiProcessorCount * 32);   /* resident blocks */
         if (threads < 1) { sim->err = "not enough device memory for one U0 live list"; return RA_E_NOMEM; }
-        d.grid = (int)((threads + RA_U0_NT - 1) / RA_U0_NT);
+        d.grid = (int)threads;
         d.smem = 0;
-        cudaError_t e = cudaMalloc(&d.dWorkspace, perThread * (size_t)d.grid * RA_U0_NT);
+        cudaError_t e = cudaMalloc(&d.dWorkspace, perThread * (size_t)d.grid);
         if (e != cudaSuccess) { sim->err = std::string("U0 workspace cudaMalloc failed: ") + cudaGetErrorString(e); return RA_E_NOMEM; }
         return RA_OK;
     }
@@ -658,10 +658,12 @@ extern "C" int ra_sim_run(ra_sim* sim) {
         a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
         a.liveBase = (RuUE*)d.dWorkspace;
         if (sim->variant == RA_VARIANT_U0) {
-            const int heads = sim->maxR <= 64;      /* phantom calendar heads in shared memory unless BI is huge */
+            const int heads = sim->maxR <= 1024;    /* phantom calendar heads in shared memory unless BI is huge */
             const size_t sm = ru_smem_bytes(sim->maxR, heads != 0);
-            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, RA_U0_NT, sm, d.stream>>>(a, sim->cap, heads);
-            else ra_u0_kernel<false><<<d.grid, RA_U0_NT, sm, d.stream>>>(a, sim->cap, heads);
+            const char* mode = getenv("RACH_U0");   /* RACH_U0=serial: the one-thread formulation, for cross-checks */
+            const int lanesOn = !(mode && mode[0] == 's');
+            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
+            else ra_u0_kernel<false><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
         } else {
             void* kargs[] = {&a};
             RA_CUDA(sim, cudaLaunchKernel(d.kern, dim3(d.grid), dim3(d.nt), kargs, d.smem, d.stream));

@@ -186,6 +186,8 @@ extern "C" int emu_run_n(const ref_config* cfg, ref_result* res, int* perUE, flo
  * ------------------------------------------------------------------------------------------ */
 #include "rach_core_u0.cuh"
 
+extern "C" { int emu_u0_mode = 1; }
+
 extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, float* geom) {
     (void)geom;
     ra_params p; ra_params_default(&p, RA_VARIANT_U0);
@@ -199,9 +201,11 @@ extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, fl
     std::vector<int> phHead((size_t)pt.R);
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = perUE;
     RuStats st;
-    std::vector<RuUE> win(5);                      /* a 5-entry window: both halves of the split live list are exercised */
-    if (perUE) ru_run_replication<true>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, &st);
-    else ru_run_replication<false>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, &st);
+    /* emu_u0_mode 1: the warp step (32 lanes played by a loop), 40-entry window so that crowded ms spill to the
+     * global list; 0: the serial step in every ms, 5-entry window */
+    std::vector<RuUE> win(emu_u0_mode ? 40 : 5);
+    if (perUE) ru_run_replication<true>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, emu_u0_mode, &st);
+    else ru_run_replication<false>(job, live.data(), win.data(), (int)win.size(), ph.data(), phHead.data(), pt.nUE, emu_u0_mode, &st);
     memset(res, 0, sizeof *res);
     res->simTimeMs = st.simTime; res->nSuccess = st.nSuccess; res->preambleTxSum = st.txSum; res->delaySum = st.delaySum;
     res->collisionPreambles = st.collisionPreambles; res->totalPreambleTxop = st.totalPreambleTxop;

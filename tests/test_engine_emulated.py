@@ -98,11 +98,17 @@ def test_noma_variant_emulated(oracle, emu):
 
 
 def test_legacy_variant_emulated(oracle, emu):
-    """Variant U0 (rach_core_u0.cuh, one thread per replication) on the host against the U0 oracle."""
+    """Variant U0 (rach_core_u0.cuh) on the host against the U0 oracle: the warp step (one lane per live UE, the 32
+    lanes played by a loop over the same source the device compiles; crowded ms fall back to the serial step) and
+    the serial step alone."""
+    import ctypes
     so = os.path.join(ROOT, "tests", "emu", "_build", "librach_emu.so")
     f = oracle._lib(so, "emu_run_u0")
+    mode = ctypes.c_int.in_dll(ctypes.CDLL(so), "emu_u0_mode")
     rnd = random.Random(8)
-    cases = [dict(nUE=2000), dict(nUE=20000, seed=2), dict(nUE=40000, nPreamble=1, seed=3)]
+    cases = [dict(nUE=2000), dict(nUE=20000, seed=2), dict(nUE=40000, nPreamble=1, seed=3),
+             dict(nUE=250000, nPreamble=64, backoffIndicator=2, seed=327613445147561757, rep=601, stopMs=6000),   # > 32 live
+             dict(nUE=120000, nPreamble=16, backoffIndicator=1, seed=264716576123012100, rep=650, stopMs=3000)]
     for _ in range(25):
         cases.append(dict(nUE=rnd.choice([1, 2, 50, 400, 3000, 9000, 40000]), nPreamble=rnd.choice([1, 2, 3, 8, 64]),
                           backoffIndicator=rnd.choice([1, 2, 5, 20, 40]), seed=rnd.getrandbits(60), rep=rnd.randrange(1000),
@@ -110,10 +116,13 @@ def test_legacy_variant_emulated(oracle, emu):
     for kw in cases:
         cfg = oracle.make_config_u0(**kw)
         p, ue = oracle.run_port_u0(cfg)
-        e, ue2, _ = oracle._run(f, cfg, True, False)
-        for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop"):
-            assert getattr(p, k) == getattr(e, k), (k, kw)
-        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+        for md in (1, 0):
+            mode.value = md
+            e, ue2, _ = oracle._run(f, cfg, True, False)
+            for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop"):
+                assert getattr(p, k) == getattr(e, k), (k, md, kw)
+            np.testing.assert_array_equal(ue, ue2, err_msg="%s mode %d" % (kw, md))
+    mode.value = 1
 
 
 def test_work_list_overflow_paths(oracle, tmp_path):

@@ -309,7 +309,7 @@ def test_legacy_u0_fixtures_and_fuzz(pkg, golden, oracle):
 
 def test_legacy_u0_batch_full_size(pkg, oracle):
     """RandomAccessSimulator.c as shipped at 100 000 UEs (9 arrivals per 5 ms, 64 preambles): 32 replications
-    in one launch (one thread each); three of them checked UE by UE."""
+    in one launch (one warp each); three of them checked UE by UE."""
     p = pkg.default_params(variant=1, nUE=100000, seed=4)
     with pkg.RachSim([p], reps=32, devices=[0], rep_offset=10, dump_ues=True) as sim:
         sim.run()
@@ -320,3 +320,25 @@ def test_legacy_u0_batch_full_size(pkg, oracle):
         res, ue_ref = oracle.run_port_u0(oracle.make_config_u0(nUE=100000, seed=4, rep=10 + r))
         assert int(st[0, r]["simTimeMs"]) == res.simTimeMs and int(st[0, r]["delaySum"]) == res.delaySum
         np.testing.assert_array_equal(ue, ue_ref)
+
+
+def test_legacy_u0_serial_formulation_and_crowded_ms(pkg, oracle, monkeypatch):
+    """U0 has two exact formulations of a ms (warp step: one lane per live UE; serial step: lane 0 walks the list,
+    used for ms with more than 32 live UEs).  RACH_U0=serial forces the serial one everywhere; a 250 000-UE
+    population (21 arrivals per 5 ms) mixes both; an overload with one preamble exercises the phantom calendar."""
+    cases = [dict(nUE=9000, seed=21), dict(nUE=250000, nPreamble=64, backoffIndicator=2, seed=22),
+             dict(nUE=30000, nPreamble=1, seed=23)]
+    refs = []
+    for kw in cases:
+        p = pkg.default_params(variant=1, **kw)
+        p.maxTimeMs = 5000
+        refs.append((p, oracle.run_port_u0(oracle.make_config_u0(stopMs=5000, **kw))))
+    for mode in ("warp", "serial"):
+        monkeypatch.setenv("RACH_U0", mode)
+        with pkg.RachSim([p for p, _ in refs], reps=1, devices=[0], dump_ues=True) as sim:
+            sim.run()
+            for k, (p, (res, ue_ref)) in enumerate(refs):
+                st, ue = sim.stats(k, 0), sim.dump_ues(k, 0)
+                for key in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "collisionPreambles", "totalPreambleTxop"):
+                    assert getattr(st, key) == getattr(res, key), (mode, key, cases[k])
+                np.testing.assert_array_equal(ue, ue_ref, err_msg="%s %s" % (mode, cases[k]))
