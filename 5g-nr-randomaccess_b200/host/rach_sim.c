@@ -12,6 +12,11 @@
  *                               file line that carries the kernel time of the whole launch);
  *                           n = NOMA.c:598-635,712-716 (variant N: "nUE nSuccess ratio meanTx meanDelay",
  *                               appended to TestResults/Sector_<nUE>_Result.txt, "Done" after each seed)
+ *                           u = RandomAccessSimulator.c:69-70,141-143,277-345 (variant U0: 64 preambles, no seed loop,
+ *                               the two "Result" banners, 2_SimulationResults/2_Exclude_msg2_failures_UE<nUE>_*;
+ *                               its collision / tx-opportunity counters are globals that the file never resets,
+ *                               so they accumulate over the sweep -- reproduced; U0:321 does not compile as
+ *                               shipped: read as a plain assignment to the parameter)
  *           --nue a,b,c  (points; default the reference sweep 10000..100000 step 10000, W:221)
  *           --no-logs    (skip the per-UE *_Logs.txt, W:797-825)
  *           --outdir DIR (default "."), --device N, --seed64 S (tape key, default 0)
@@ -60,6 +65,92 @@ static void usage_and_exit(void) {
     exit(-1);
 }
 
+/* --format u: the report of RandomAccessSimulator.c (U0:42-143 main, U0:277-345 writers), one replication per point */
+static int report_u0(const ra_params* base, const int* nueList, int nNue, const char* outdir, int writeLogs, int device,
+                     int preambleSet, int backoffSet) {
+    ra_params* pts = (ra_params*)calloc((size_t)nNue, sizeof *pts);
+    for (int k = 0; k < nNue; ++k) {
+        ra_params_default(&pts[k], RA_VARIANT_U0);                    /* U0:48-59: 64 preambles, BI 20, 60 s */
+        if (preambleSet) pts[k].nPreamble = base->nPreamble;
+        if (backoffSet) pts[k].backoffIndicator = base->backoffIndicator;
+        pts[k].seed = base->seed; pts[k].nUE = nueList[k];
+    }
+    char dir[600];
+    snprintf(dir, sizeof dir, "%s/2_SimulationResults", outdir);
+    mkdir(outdir, 0755);
+    mkdir(dir, 0755);
+    ra_options opt; memset(&opt, 0, sizeof opt);
+    opt.dumpUEs = 1;                                                  /* the delay sum is a float accumulation in UE order */
+    ra_sim* sim = ra_sim_create_ex(pts, nNue, 1, &device, 1, &opt);
+    if (!sim) { fprintf(stderr, "rach_sim: %s\n", ra_last_create_error()); return 2; }
+    if (ra_sim_run(sim) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+    int collisionPreambles = 0, totalPreambleTxop = 0;                /* U0:36-37: globals, never reset */
+    for (int k = 0; k < nNue; ++k) {
+        const int nUE = pts[k].nUE, maxTime = 60000, accessTime = 5;
+        int nAccessUE = ceil((float)nUE * (float)accessTime * 1.0 / (float)maxTime);   /* U0:60 */
+        if (nAccessUE == 0) nAccessUE = 1;
+        printf("-------- %05d Result ---------\n", nUE);                               /* U0:69-70 */
+        printf("%d\n", nAccessUE);
+        ra_stats st;
+        if (ra_sim_stats(sim, k, 0, &st) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+        int* ue = (int*)malloc(sizeof(int) * (size_t)nUE * RA_DUMP_FIELDS);
+        if (ra_sim_dump_ues(sim, k, 0, ue) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+        const int time = st.simTimeMs;
+        const int lastMs = time < maxTime ? time : maxTime - 1;
+        int activeCheck = 0;
+        for (int t = 1; t <= lastMs; t += accessTime) {                                /* U0:77-81 */
+            if (activeCheck >= nUE) activeCheck = nUE; else activeCheck += nAccessUE;
+        }
+        float averageDelay = 0; int failedUEs = 0, preambleTxCount = 0;                /* U0:127-139 */
+        for (int i = 0; i < nUE; ++i) {
+            const int* r = ue + (size_t)i * RA_DUMP_FIELDS;
+            if (r[10] == 0) failedUEs++;
+            else { averageDelay += (float)r[0]; preambleTxCount += r[7]; }
+        }
+        const int nSuccessUE = st.nSuccess;
+        collisionPreambles += (int)st.collisionPreambles; totalPreambleTxop += (int)st.totalPreambleTxop;
+        printf("-------- %05d Result ---------\n", activeCheck);                       /* U0:141 */
+        char path[800], buf[1000];
+        snprintf(path, sizeof path, "%s/2_Exclude_msg2_failures_UE%05d_Results.txt", dir, nUE);   /* U0:282 */
+        FILE* fp = fopen(path, "w+");
+        if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
+#define U0_LINE(...) do { snprintf(buf, sizeof buf, __VA_ARGS__); fputs(buf, stdout); fputs(buf, fp); } while (0)
+        U0_LINE("Number of UEs: %d\n", nUE);
+        U0_LINE("Total simulation time: %dms\n", time);
+        U0_LINE("Number of succeed UEs: %d\n", nSuccessUE);
+        float ratioSuccess = (float)nSuccessUE / (float)nUE;
+        U0_LINE("Success ratio: %lf\n", ratioSuccess);
+        U0_LINE("Number of failed UEs: %d\n", failedUEs);
+        float ratioFailed = (float)failedUEs / (float)nUE;
+        U0_LINE("Fail probability: %lf\n", ratioFailed);
+        float nCollisionPreambles = (float)collisionPreambles / (float)preambleTxCount;
+        U0_LINE("Number of collision preambles: %lf\n", nCollisionPreambles);
+        float averagePreambleTx = (float)totalPreambleTxop / (float)nSuccessUE;
+        U0_LINE("Average preamble tx count: %lf\n", averagePreambleTx);
+        averageDelay = averageDelay / (float)nSuccessUE;                               /* U0:321, see the header */
+        U0_LINE("Average delay: %lfms\n", averageDelay);
+#undef U0_LINE
+        fclose(fp);
+        if (writeLogs) {                                                               /* U0:328-345 */
+            snprintf(path, sizeof path, "%s/2_Exclude_msg2_failures_UE%05d_Logs.txt", dir, nUE);
+            fp = fopen(path, "w+");
+            if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
+            for (int i = 0; i < nUE; ++i) {
+                const int* r = ue + (size_t)i * RA_DUMP_FIELDS;
+                fprintf(fp, "Idx: %d | Timer: %d | Active: %d | txTime: %d | Preamble: %d | Preamble change: %d | RAR window: %d | "
+                            "Max RAR: %d | Preamble reTx: %d | MSG 2 Flag: %d | ConnectRequest: %d | MSG 4 Flag: %d\n",
+                        i, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r[8], r[9], r[10]);
+            }
+            fclose(fp);
+        }
+        free(ue);
+    }
+    fprintf(stderr, "rach_sim: %d points, kernel %.1f ms (%s)\n", nNue, ra_sim_kernel_ms(sim), ra_version());
+    ra_sim_destroy(sim);
+    free(pts);
+    return 0;
+}
+
 static int is_flag(const char* a, const char* l, const char* s, const char* alias) {
     return strcmp(a, l) == 0 || strcmp(a, s) == 0 || (alias && strcmp(a, alias) == 0);
 }
@@ -67,7 +158,7 @@ static int is_flag(const char* a, const char* l, const char* s, const char* alia
 int main(int argc, char* argv[]) {
     ra_params base;
     ra_params_default(&base, RA_VARIANT_W);
-    int times = 1, writeLogs = 1, device = 0, grantSet = 0;
+    int times = 1, writeLogs = 1, device = 0, grantSet = 0, preambleSet = 0, backoffSet = 0;
     char format = 'w';
     const char* outdir = ".";
     int nueList[64], nNue = 0;
@@ -85,10 +176,10 @@ int main(int argc, char* argv[]) {
             base.distribution = atoi(v);
         } else if (is_flag(a, "--preambles", "-p", NULL)) {
             if (atoi(v) < 1) die("Number of preamble must be greater than zero.");
-            base.nPreamble = atoi(v);
+            base.nPreamble = atoi(v); preambleSet = 1;
         } else if (is_flag(a, "--backoff", "-b", NULL)) {
             if (atoi(v) < 1) die("Backoff indicator must be greater than zero.");
-            base.backoffIndicator = atoi(v);
+            base.backoffIndicator = atoi(v); backoffSet = 1;
         } else if (is_flag(a, "--grant", "-g", NULL)) {
             if (atoi(v) < 1) die("The number of Up Link Grant per RAR must be greater than zero.");
             base.nGrantUL = atoi(v); grantSet = 1;
@@ -122,7 +213,8 @@ int main(int argc, char* argv[]) {
     }
     if (nNue == 0) for (int n = 10000; n <= 100000; n += 10000) nueList[nNue++] = n;   /* W:221 */
     base.seed = seed64;
-    if (format != 'w' && format != 'b' && format != 'n') usage_and_exit();
+    if (format != 'w' && format != 'b' && format != 'n' && format != 'u') usage_and_exit();
+    if (format == 'u') return report_u0(&base, nueList, nNue, outdir, writeLogs, device, preambleSet, backoffSet);
     if (format == 'b') { base.geometry = 0; if (!grantSet) base.nGrantUL = 54; }         /* B:49, B:137-145 */
     if (format == 'n') {                                                                 /* NOMA.c:41-57 */
         ra_params n; ra_params_default(&n, RA_VARIANT_N);

@@ -81,13 +81,14 @@ SWEEP='s/for (int n = 10000; n <= 100000; n += 10000)/for (int n = ref_nue; n <=
 # ---- U0: RandomAccessSimulator.c ----------------------------------------------------------
 #   U0:42  nUE sweep -> ref_nue;  U0:48-49 parameter locals -> ref_p_*
 #   U0:84  `i <= activeCheck` reads one element past the array once activeCheck reaches nUE -> clamp
-#   U0:321 `float averageDelay = averageDelay/...` redeclares the parameter (does not compile) -> renamed
+#   U0:321 `float averageDelay = averageDelay/...` redeclares the parameter (does not compile) -> the `float` dropped
+#          (plain assignment to the parameter, so that U0:322-323 report the average as the text says)
 { echo '#include "ref_shim_pre.h"'
   sed -e '42s/for(int n = 10000; n <= 100000; n+=10000)/for(int n = ref_nue; n <= ref_nue; n+=10000)/' \
       -e '48s/int nPreamble = 64;/int nPreamble = ref_p_nPreamble;/' \
       -e '49s/int backoffIndicator = 20;/int backoffIndicator = ref_p_backoff;/' \
       -e '84s/i <= activeCheck/i <= activeCheck \&\& i < nUE/' \
-      -e '321s/float averageDelay = averageDelay/float averageDelay_ = averageDelay/' \
+      -e '321s/float averageDelay = averageDelay/averageDelay = averageDelay/' \
       "$ref/RandomAccessSimulator.c"
   echo; echo '#include "ref_shim_post_u0.h"'
 } | $CC $CFLAGS -x c - -o "$out/libref_u0.so" -lm

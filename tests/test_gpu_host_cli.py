@@ -143,3 +143,53 @@ def test_format_n_matches_noma_c(tmp_path, oracle):
     assert out == exp
     for n in nues:
         assert (tmp_path / "ours" / "TestResults" / ("Sector_%d_Result.txt" % n)).read_text() == files[n]
+
+
+REF_SCRIPT_U0 = r'''
+import sys
+sys.path.insert(0, %r)
+from oracle import oracle as O
+r, _ = O.run_ref_u0(O.make_config_u0(nUE=int(sys.argv[1]), rep=0, echo=2))
+print("COUNTERS %%d %%d %%d %%d" %% (r.collisionPreambles, r.totalPreambleTxop, r.preambleTxSum, r.nSuccess))
+''' % ROOT
+
+
+def test_format_u_matches_random_access_simulator_c(tmp_path, oracle):
+    """--format u: the report of RandomAccessSimulator.c (U0:69-70, 141-143, 277-345): stdout, *_Results.txt and
+    *_Logs.txt byte for byte against the tape-mode build of that file; its collision / tx-opportunity counters are
+    globals that accumulate over the nUE sweep (U0:36-37), so the second point's two ratio lines are checked
+    against the sums."""
+    import numpy as np
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_u0.so")):
+        pytest.skip("oracle/_ref/libref_u0.so not shipped")
+    pkg = importlib.import_module("5g-nr-randomaccess_b200")
+    exe = pkg.build_host()
+    nues = [20000, 30000]
+    out = subprocess.run([exe, "--format", "u", "--nue", ",".join(map(str, nues)), "--outdir", str(tmp_path / "ours")],
+                         capture_output=True, text=True, check=True).stdout
+    refs = []
+    for n in nues:
+        d = tmp_path / ("refu_%d" % n)
+        (d / "2_SimulationResults").mkdir(parents=True)
+        ro = subprocess.run([sys.executable, "-c", REF_SCRIPT_U0, str(n)], cwd=d, capture_output=True, text=True, check=True).stdout
+        body, counters = ro.rsplit("COUNTERS ", 1)
+        refs.append((d, body, [int(x) for x in counters.split()]))
+    # first point: everything identical
+    assert out.startswith(refs[0][1])
+    for kind in ("Results", "Logs"):
+        name = "2_Exclude_msg2_failures_UE%05d_%s.txt" % (nues[0], kind)
+        assert (tmp_path / "ours" / "2_SimulationResults" / name).read_bytes() == (refs[0][0] / "2_SimulationResults" / name).read_bytes(), name
+    # second point: the per-UE log is identical; the report differs only in the two lines fed by the global counters
+    ours2 = out[len(refs[0][1]):].split("\n")
+    ref2 = refs[1][1].split("\n")
+    (c1, t1, _, _), (c2, t2, tx2, ns2) = refs[0][2], refs[1][2]
+    f32 = np.float32
+    exp = list(ref2)
+    for i, line in enumerate(ref2):
+        if line.startswith("Number of collision preambles:"):
+            exp[i] = "Number of collision preambles: %f" % float(f32(c1 + c2) / f32(tx2))
+        if line.startswith("Average preamble tx count:"):
+            exp[i] = "Average preamble tx count: %f" % float(f32(t1 + t2) / f32(ns2))
+    assert ours2 == exp
+    name = "2_Exclude_msg2_failures_UE%05d_Logs.txt" % nues[1]
+    assert (tmp_path / "ours" / "2_SimulationResults" / name).read_bytes() == (refs[1][0] / "2_SimulationResults" / name).read_bytes()
