@@ -87,7 +87,7 @@ typedef struct ra_stats {
     long long preambleTxSum;     /* sum of preambleTxCounter over msg4Flag==1, W:347           */
     long long delaySum;          /* sum of timer over msg4Flag==1, W:346 (float in the ref.)   */
     long long failCountSum;      /* sum of failCount over msg4Flag==1, W:348                   */
-    long long continueFailed;    /* continueFaliedUEs, W:499,682                               */
+    long long continueFailed;    /* continueFaliedUEs, W:499,682 (U0: drops, raFailed = -1, U0:181-184)  */
     long long finalSuccess;      /* finalSuccessUEs, W:676                                     */
     long long collisionPreambles;/* W:62,650  (+= group size per collided scan)                */
     long long totalPreambleTxop; /* W:63,625,652                                               */
@@ -96,7 +96,11 @@ typedef struct ra_stats {
     long long updates;           /* nUE * ceil(simTimeMs / accessTime): the throughput unit    */
 } ra_stats;
 
-/* Engine options (all zero = defaults). */
+/* Engine options (all zero = defaults).
+ * Tuning / cross-check switches read from the environment at create / run time, never needed in normal use:
+ *   RACH_BLOCK=big|small   force one of the two block shapes of the W step kernel (256 x 5 / 128 x 8 per SM)
+ *   RACH_U0=serial         variant U0: the one-lane serial step in every ms instead of the warp step
+ *   RACH_CARVEOUT=<pct>    preferred shared-memory carveout of the step kernel */
 typedef struct ra_options {
     int repOffset;      /* tape replication id of local rep 0 (multi-process sharding)        */
     int dumpUEs;        /* 1 = keep the 16-int per-UE final record of every replication       */
