@@ -51,10 +51,10 @@ class RaOptions(C.Structure):
                 ("phaseTimers", C.c_int), ("reserved", C.c_int * 4)]
 
 
-SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_sim_run", "ra_sim_stats",
+SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_last_create_code", "ra_sim_run", "ra_sim_stats",
            "ra_sim_stats_all", "ra_sim_dump_ues", "ra_sim_geometry", "ra_sim_gains", "ra_sim_kernel_ms",
            "ra_sim_gpu_launches", "ra_sim_phase_cycles", "ra_sim_destroy", "ra_sim_last_error", "ra_params_default",
-           "ra_horizon_ms", "ra_arrival_schedule", "ra_version"]
+           "ra_horizon_ms", "ra_arrival_schedule", "ra_params_validate", "ra_version"]
 
 _lib = None
 
@@ -97,6 +97,7 @@ def load_lib():
     lib.ra_params_default.argtypes = [C.POINTER(RaParams), C.c_int]
     lib.ra_horizon_ms.argtypes = [C.POINTER(RaParams)]
     lib.ra_arrival_schedule.argtypes = [C.POINTER(RaParams), vp, C.c_int]
+    lib.ra_params_validate.argtypes = [C.POINTER(RaParams), C.c_char_p, C.c_int]
     lib.ra_version.restype = C.c_char_p
     _lib = lib
     return lib
@@ -111,6 +112,13 @@ def default_params(**kw):
             raise AttributeError(k)
         setattr(p, k, v)
     return p
+
+
+def validate_params(params):
+    """(RA_OK, "") or (RA_E_INVAL, reason): the checks ra_sim_create applies, without a device."""
+    buf = C.create_string_buffer(256)
+    rc = load_lib().ra_params_validate(C.byref(params), buf, 256)
+    return rc, buf.value.decode()
 
 
 def arrival_schedule(params):
@@ -138,7 +146,7 @@ class RachSim:
             dev, nd = (C.c_int * len(devices))(*devices), len(devices)
         self._h = lib.ra_sim_create_ex(arr, len(self.points), self.reps, dev, nd, C.byref(opt))
         if not self._h:
-            raise RachError("ra_sim_create failed: %s" % lib.ra_last_create_error().decode())
+            raise RachError("ra_sim_create failed (%d): %s" % (lib.ra_last_create_code(), lib.ra_last_create_error().decode()))
 
     def _check(self, rc):
         if rc != 0:

@@ -1,4 +1,5 @@
 """Build librach_gpu.so (in-tree, sm_100a) and the host CLI.  nvcc cross-compiles without a GPU."""
+import glob
 import os
 import shutil
 import subprocess
@@ -8,8 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "librach_gpu.so")
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("rach_engine.cu", "rach_host.cpp")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("rach_core.cuh", "rach_host.h")] + \
-          [os.path.join(ROOT, "include", f) for f in ("rach_gpu.h", "rach_tape.h")]
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh")) + glob.glob(os.path.join(HERE, "csrc", "*.h")) +
+                 glob.glob(os.path.join(ROOT, "include", "*.h")))
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
               "-I", os.path.join(HERE, "csrc")]

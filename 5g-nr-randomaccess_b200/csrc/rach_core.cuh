@@ -84,7 +84,8 @@ template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) 
 struct RaPointDev {
     int nUE, P, BI, G, Wn, M, A, maxTime;
     int geometry, R, nOcc, hshift;  /* hshift: idx >> hshift < RA_HBINS */
-    unsigned magicBI, magicP, magicA, pad; /* ra_magic() of the three runtime divisors */
+    unsigned magicBI, magicP, magicA;      /* ra_magic() of the three runtime divisors */
+    float cellRadius;                      /* variant N: per point (N:56, used by activeUE N:168) */
     ra_u64 seed;
     const int* arrCum;        /* [nOcc] activeCheck after the arrival step of ms occ*A (W:280-292) */
     /* byte offsets of the block's tables in dynamic shared memory (ra_layout): a function of (R, P) only, kept

@@ -144,8 +144,10 @@ RA_HD void rn_phaseA0(const RaJob& job, RaSharedN& s, int T, int tid, int nt) {
 
 /* ---- occasion phase A1: activeUE N:131-192 for the new arrivals; they transmit in this occasion ---- */
 template <bool DUMP>
-RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, unsigned item, float cellRadius) {
+#define RN_MAX_REJECT 65536   /* draws one rejection loop of activeUE may take before the engine gives up (RA_E_INTERNAL) */
+RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, unsigned item) {
     const RaPointDev& pt = *job.pt;
+    const float cellRadius = pt.cellRadius;
     const unsigned idx = (unsigned)s.acOld + item;
     RaStream st = ra_stream(job, idx, T);
     const float pi = 3.14;
@@ -154,14 +156,18 @@ RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int
     const float angle = (float)ra / (float)(2147483647) * 2 * pi;
     const int sector = ra_sector(ra);                                                              /* N:146-163 */
     float r;
-    for (;;) {                                                                                     /* N:167-172 */
+    /* the reference's loops have no bound; validation keeps the radius where they end quickly, the cap only turns a
+     * hang on absurd parameters into an error */
+    for (int it = 0;; ++it) {                                                                      /* N:167-172 */
         r = (float)((double)cellRadius * sqrt((double)((float)ra_stream_next(st) / (float)2147483647)));
         if ((double)r > 35.0) break;
+        if (it >= RN_MAX_REJECT) { s.overflow = 3; break; }
     }
     const float x = (float)((double)r * cos((double)angle)), y = (float)((double)r * sin((double)angle));   /* N:176,178 */
     const double env = sqrt((double)RA_FADD(RA_FMUL(x, x), RA_FMUL(y, y)));                         /* N:183 */
     double ch_g = 0;
-    while (ch_g < 1e-7) {                                                                          /* N:185-189 */
+    for (int it = 0; ch_g < 1e-7; ++it) {                                                          /* N:185-189 */
+        if (it >= RN_MAX_REJECT) { s.overflow = 3; break; }
         const float pathloss = (float)sqrt(RA_DADD(1.0, RA_DMUL(env, env)));
         const double rayleigh = sqrt(RA_DMUL(-2.0, log((double)ra_stream_next(st) / (double)2147483647)));
         const double q = rayleigh / (double)pathloss;

@@ -57,7 +57,6 @@ struct RaKernelArgs {
     const unsigned*   jobRep;       /* [nJobs] tape replication id               */
     const RaWork*     works;        /* [gridDim.x]  (variant W)                  */
     const RaWorkN*    worksN;       /* [gridDim.x]  (variant N)                  */
-    float             cellRadius;   /* variant N (N:56)                          */
     double*           gainDump;     /* [nJobs][cap] channelGain per UE (variant N, DUMP) or NULL */
     RuUE*             liveBase;     /* [threads][cap] live lists (variant U0)    */
     size_t            gainStride;
@@ -257,7 +256,7 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
             if (T % pt.A == 0) {                                        /* a RACH occasion, N:668 */
                 rn_phaseA0(job, s, T, tid, nt);
                 __syncthreads();
-                for (unsigned i = tid; i < (unsigned)s.nArr; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i, a.cellRadius);
+                for (unsigned i = tid; i < (unsigned)s.nArr; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i);
                 __syncthreads();
                 const unsigned nTx = s.bcount[(unsigned)T & Rm];
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
@@ -384,6 +383,7 @@ struct RaDev {
     int grid = 0, nt = 0; size_t smem = 0; const void* kern = nullptr;
     cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<ra_stats> hStats;
+    int hErr = 0;
 };
 
 static const void* ra_step_entry(bool dump, bool big) {
@@ -409,6 +409,7 @@ struct ra_sim {
 
 
 static thread_local std::string g_createErr;
+static thread_local int g_createCode = RA_OK;
 
 #define RA_CUDA(sim, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -568,14 +569,15 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
 }
 
 extern "C" const char* ra_last_create_error(void) { return g_createErr.c_str(); }
+extern "C" int ra_last_create_code(void) { return g_createCode; }
 
 extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int repsPerPoint,
                                     const int* devices, int nDevices, const ra_options* opt) {
-    g_createErr.clear();
+    g_createErr.clear(); g_createCode = RA_E_INVAL;      /* every early return below is a parameter error unless it says otherwise */
     if (!points || nPoints < 1 || repsPerPoint < 1) { g_createErr = "points/nPoints/repsPerPoint invalid"; return nullptr; }
     int devCount = 0;
     if (cudaGetDeviceCount(&devCount) != cudaSuccess || devCount < 1) {
-        g_createErr = "no CUDA device: librach_gpu has no CPU path"; return nullptr;
+        g_createErr = "no CUDA device: librach_gpu has no CPU path"; g_createCode = RA_E_NODEVICE; return nullptr;
     }
     ra_sim* sim = new ra_sim();
     memset(&sim->opt, 0, sizeof sim->opt);
@@ -594,7 +596,7 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
         pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
         pt.maxTime = ra_horizon_ms(&p); pt.geometry = p.geometry ? 1 : 0; pt.R = ra_host_ring(&p);
-        pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.arrCum = nullptr;
+        pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.arrCum = nullptr; pt.cellRadius = p.cellRadius;
         ra_host_fill_point(&pt);
         if (p.variant == RA_VARIANT_U0) ra_host_point_u0(&p, &pt);
         sim->hostPoints.push_back(pt);
@@ -629,8 +631,9 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
     sim->stats.resize(nJobs);
     for (RaDev& d : sim->devs) {
         int rc = ra_setup_device(sim, d);
-        if (rc != RA_OK) { g_createErr = sim->err; ra_sim_destroy(sim); return nullptr; }
+        if (rc != RA_OK) { g_createErr = sim->err; g_createCode = rc; ra_sim_destroy(sim); return nullptr; }
     }
+    g_createCode = RA_OK;
     return sim;
 }
 
@@ -639,55 +642,83 @@ extern "C" ra_sim* ra_sim_create(const ra_params* points, int nPoints, int repsP
     return ra_sim_create_ex(points, nPoints, repsPerPoint, devices, nDevices, nullptr);
 }
 
+/* launch on one device (asynchronous); the caller synchronises */
+static int ra_launch_device(ra_sim* sim, RaDev& d) {
+    const int nJobs = (int)d.jobs.size();
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
+    RA_CUDA(sim, cudaMemsetAsync(d.dErr, 0, sizeof(int), d.stream));
+    RA_CUDA(sim, cudaMemsetAsync(d.dCyc, 0, sizeof(ra_u64) * RA_NPHASE, d.stream));
+    RaKernelArgs a; memset(&a, 0, sizeof a);
+    a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
+    a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = sim->opt.phaseTimers ? d.dCyc : nullptr;
+    a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
+    RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
+    a.worksN = d.dWorksN;
+    a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
+    a.liveBase = (RuUE*)d.dWorkspace;
+    if (sim->variant == RA_VARIANT_U0) {
+        const int heads = sim->maxR <= 1024;    /* phantom calendar heads in shared memory unless BI is huge */
+        const size_t sm = ru_smem_bytes(sim->maxR, heads != 0);
+        const char* mode = getenv("RACH_U0");   /* RACH_U0=serial: the one-thread formulation, for cross-checks */
+        const int lanesOn = !(mode && mode[0] == 's');
+        if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
+        else ra_u0_kernel<false><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
+    } else {
+        void* kargs[] = {&a};
+        RA_CUDA(sim, cudaLaunchKernel(d.kern, dim3(d.grid), dim3(d.nt), kargs, d.smem, d.stream));
+    }
+    RA_CUDA(sim, cudaGetLastError());
+    RA_CUDA(sim, cudaEventRecord(d.e1, d.stream));
+    RA_CUDA(sim, cudaMemcpyAsync(d.hStats.data(), d.dStats, sizeof(ra_stats) * nJobs, cudaMemcpyDeviceToHost, d.stream));
+    RA_CUDA(sim, cudaMemcpyAsync(&d.hErr, d.dErr, sizeof(int), cudaMemcpyDeviceToHost, d.stream));
+    return RA_OK;
+}
+
+/* wait for one device and collect its results */
+static int ra_collect_device(ra_sim* sim, RaDev& d, double* ms) {
+    RA_CUDA(sim, cudaSetDevice(d.id));
+    RA_CUDA(sim, cudaStreamSynchronize(d.stream));
+    float t = 0; RA_CUDA(sim, cudaEventElapsedTime(&t, d.e0, d.e1));
+    *ms = std::max(*ms, (double)t);
+    if (d.hErr) {
+        sim->err = d.hErr == 1 ? "engine self-check: a calendar bucket overflowed"
+                 : d.hErr == 3 ? "engine self-check: a rejection loop of activeUE (NOMA.c:167-172, 185-189) did not end within 65536 draws"
+                 : "engine self-check: a packed per-UE counter overflowed (preambleTxCounter > 32767, failCount > 65535)";
+        return RA_E_INTERNAL;
+    }
+    for (size_t j = 0; j < d.jobs.size(); ++j) sim->stats[d.jobs[j]] = d.hStats[j];
+    return RA_OK;
+}
+
 extern "C" int ra_sim_run(ra_sim* sim) {
     if (!sim) return RA_E_INVAL;
-    sim->launches = 0;
-    for (RaDev& d : sim->devs) {
-        const int nJobs = (int)d.jobs.size();
-        if (!nJobs) continue;
-        RA_CUDA(sim, cudaSetDevice(d.id));
-        RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
-        RA_CUDA(sim, cudaMemsetAsync(d.dErr, 0, sizeof(int), d.stream));
-        RA_CUDA(sim, cudaMemsetAsync(d.dCyc, 0, sizeof(ra_u64) * RA_NPHASE, d.stream));
-        RaKernelArgs a; memset(&a, 0, sizeof a);
-        a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
-        a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = sim->opt.phaseTimers ? d.dCyc : nullptr;
-        a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
-        RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
-        a.worksN = d.dWorksN; a.cellRadius = sim->points[0].cellRadius;
-        a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
-        a.liveBase = (RuUE*)d.dWorkspace;
-        if (sim->variant == RA_VARIANT_U0) {
-            const int heads = sim->maxR <= 1024;    /* phantom calendar heads in shared memory unless BI is huge */
-            const size_t sm = ru_smem_bytes(sim->maxR, heads != 0);
-            const char* mode = getenv("RACH_U0");   /* RACH_U0=serial: the one-thread formulation, for cross-checks */
-            const int lanesOn = !(mode && mode[0] == 's');
-            if (sim->opt.dumpUEs) ra_u0_kernel<true><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
-            else ra_u0_kernel<false><<<d.grid, 32, sm, d.stream>>>(a, sim->cap, heads, lanesOn);
-        } else {
-            void* kargs[] = {&a};
-            RA_CUDA(sim, cudaLaunchKernel(d.kern, dim3(d.grid), dim3(d.nt), kargs, d.smem, d.stream));
-        }
-        RA_CUDA(sim, cudaGetLastError());
-        RA_CUDA(sim, cudaEventRecord(d.e1, d.stream));
-        RA_CUDA(sim, cudaMemcpyAsync(d.hStats.data(), d.dStats, sizeof(ra_stats) * nJobs, cudaMemcpyDeviceToHost, d.stream));
-        sim->launches++;
+    sim->launches = 0; sim->ran = false;
+    /* every device is launched, then every launched device is drained -- also after an error, so that no stream is
+     * still writing into this handle's buffers when the caller sees the error code (and may destroy the handle) */
+    int rc = RA_OK;
+    std::string firstErr;
+    std::vector<char> launched(sim->devs.size(), 0);
+    for (size_t k = 0; k < sim->devs.size() && rc == RA_OK; ++k) {
+        RaDev& d = sim->devs[k];
+        if (d.jobs.empty()) continue;
+        d.hErr = 0;
+        launched[k] = 1;                      /* part of the sequence may be in flight even if a later call failed */
+        rc = ra_launch_device(sim, d);
+        if (rc == RA_OK) sim->launches++; else firstErr = sim->err;
     }
     double ms = 0;
-    for (RaDev& d : sim->devs) {
-        if (d.jobs.empty()) continue;
-        RA_CUDA(sim, cudaSetDevice(d.id));
-        RA_CUDA(sim, cudaStreamSynchronize(d.stream));
-        float t = 0; RA_CUDA(sim, cudaEventElapsedTime(&t, d.e0, d.e1));
-        ms = std::max(ms, (double)t);
-        int flag = 0;
-        RA_CUDA(sim, cudaMemcpy(&flag, d.dErr, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag) {
-            sim->err = flag == 1 ? "engine self-check: a calendar bucket overflowed" : "engine self-check: a packed per-UE counter overflowed (preambleTxCounter > 32767, failCount > 65535)";
-            return RA_E_INTERNAL;
+    for (size_t k = 0; k < sim->devs.size(); ++k) {
+        if (!launched[k]) continue;
+        RaDev& d = sim->devs[k];
+        if (rc == RA_OK) {
+            rc = ra_collect_device(sim, d, &ms);
+            if (rc != RA_OK) firstErr = sim->err;
+        } else {                              /* already failing: just drain */
+            cudaSetDevice(d.id); cudaStreamSynchronize(d.stream);
         }
-        for (size_t j = 0; j < d.jobs.size(); ++j) sim->stats[d.jobs[j]] = d.hStats[j];
     }
+    if (rc != RA_OK) { sim->err = firstErr; return rc; }
     sim->kernelMs = ms; sim->ran = true;
     return RA_OK;
 }

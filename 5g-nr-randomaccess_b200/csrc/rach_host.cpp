@@ -79,6 +79,9 @@ extern "C" int ra_arrival_schedule(const ra_params* p, int* arrivals, int horizo
             } else {
                 float betaDist = ra_beta_dist(3, 4, (float)time / (float)maxTime);
                 int accessUEs = (int)ceil((float)nUE * betaDist / ((float)maxTime / (float)accessTime));
+                /* a horizon beyond the reference's 10 s (maxTimeMs) puts x above 1 where (1-x)^3 < 0: nobody arrives
+                 * there (the reference never evaluates it) -- keeps the cumulative schedule monotone */
+                if (accessUEs < 0) accessUEs = 0;
                 activeCheck += accessUEs;
             }
             if (activeCheck >= nUE) activeCheck = nUE;                            /* W:290-292 */
@@ -87,6 +90,15 @@ extern "C" int ra_arrival_schedule(const ra_params* p, int* arrivals, int horizo
         }
     }
     return allAt;
+}
+
+extern "C" int ra_params_validate(const ra_params* p, char* err, int errLen) {
+    char local[256];
+    if (!p) return RA_E_INVAL;
+    const int rc = ra_host_validate(p, local, sizeof local);
+    if (rc != RA_OK && err && errLen > 0) snprintf(err, (size_t)errLen, "%s", local);
+    else if (err && errLen > 0) err[0] = 0;
+    return rc;
 }
 
 static int next_pow2(int v) { int r = 1; while (r < v) r <<= 1; return r; }
@@ -105,6 +117,10 @@ int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
         if (p->distribution == 1) RA_BAD("variant N has Beta traffic only (NOMA.c:675)");
         if (p->maxRarWindow > 5) RA_BAD("variant N: maxRarWindow %d > 5 never retransmits in NOMA.c:453-455; not supported", p->maxRarWindow);
         if (p->maxMsg2TxCount < 1) RA_BAD("variant N: maxMsg2TxCount carries maxMsg1ReTx (NOMA.c:46) and must be >= 1");
+        /* activeUE draws positions until r > 35 m and gains until >= 1e-7 (NOMA.c:167-172, 185-189): with a radius at or
+         * below 35 m the first loop never ends, beyond a few km the second practically never does */
+        if (!(p->cellRadius > 35.0f) || !(p->cellRadius <= 5000.0f))
+            RA_BAD("variant N: cellRadius %g out of range (35, 5000] m (rejection loops of NOMA.c:167-172, 185-189)", (double)p->cellRadius);
     }
     if (p->nUE < 1 || p->nUE > (1 << 24)) RA_BAD("nUE %d out of range [1, 2^24]", p->nUE);
     if (p->nPreamble < 1 || p->nPreamble > 256) RA_BAD("nPreamble %d out of range [1, 256]", p->nPreamble);
@@ -165,4 +181,4 @@ void ra_host_point_u0(const ra_params* p, RaPointDev* pt) {
     ra_host_fill_point(pt);
 }
 
-extern "C" const char* ra_version(void) { return "rach_b200 0.1 (sm_100a, variant W/B)"; }
+extern "C" const char* ra_version(void) { return "rach_b200 0.2 (sm_100a; variants W/B, U0, N)"; }

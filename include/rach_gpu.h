@@ -27,8 +27,10 @@
  * Conventions: plain pointers and sizes, caller-owned outputs, no exit() inside the
  * library (the reference's printf+exit(-1) convention, W:94-97, stays in the host main).
  * Every function that can fail returns 0 on success and a negative RA_E_* code on error;
- * ra_sim_last_error() gives the message.  There is no CPU fallback: without a CUDA
- * device ra_sim_create fails with RA_E_NODEVICE.
+ * ra_sim_last_error() gives the message.  ra_sim_create returns NULL on failure;
+ * ra_last_create_code() / ra_last_create_error() then give the RA_E_* code and the message
+ * (per calling thread).  There is no CPU fallback: without a CUDA device ra_sim_create
+ * fails with RA_E_NODEVICE.
  */
 #ifndef RACH_GPU_H
 #define RACH_GPU_H
@@ -118,6 +120,7 @@ ra_sim*     ra_sim_create(const ra_params* points, int nPoints, int repsPerPoint
 ra_sim*     ra_sim_create_ex(const ra_params* points, int nPoints, int repsPerPoint,
                              const int* devices, int nDevices, const ra_options* opt);
 const char* ra_last_create_error(void);
+int         ra_last_create_code(void);               /* RA_E_* of the last failed create on this thread, RA_OK otherwise */
 
 int         ra_sim_run(ra_sim* sim);                 /* blocking; may be called repeatedly */
 int         ra_sim_stats(ra_sim* sim, int point, int rep, ra_stats* out);
@@ -144,6 +147,9 @@ const char* ra_sim_last_error(const ra_sim* sim);
 /* Host-side helpers (no device needed). */
 int         ra_params_default(ra_params* p, int variant);   /* W:69-88 defaults */
 int         ra_horizon_ms(const ra_params* p);              /* W:243,254 */
+/* the parameter checks of ra_sim_create without a device: RA_OK, or RA_E_INVAL with the reason in err[errLen]
+ * (the reference checks only "> 0" style ranges in main, W:94-158; the engine adds its packing limits) */
+int         ra_params_validate(const ra_params* p, char* err, int errLen);
 /* arrivals[ms] for ms in [0, horizon): UEs that become active in that ms (after the clamp of
  * W:290-292), 0 for ms % accessTime != 0.  Returns the ms at which all nUE have arrived, or -1. */
 int         ra_arrival_schedule(const ra_params* p, int* arrivals, int horizon);

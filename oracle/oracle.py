@@ -37,7 +37,8 @@ class RefResult(C.Structure):
                 ("failCountsPrinted", C.c_int), ("nAccessUE", C.c_int),
                 ("averageDelay", C.c_double), ("averagePreambleTx", C.c_double),
                 ("ratioSuccess", C.c_double), ("seconds", C.c_double),
-                ("lateRestarts", C.c_longlong), ("lateAbsorbed", C.c_longlong)]
+                ("lateRestarts", C.c_longlong), ("lateAbsorbed", C.c_longlong),
+                ("pairTests", C.c_longlong), ("minPairMargin", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

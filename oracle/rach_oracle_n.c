@@ -110,6 +110,7 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
     const int maxTime = 10000;
     int activeCheck = 0, arrived = 0, nSuccess = 0, time;
     int sectorGrants[6];
+    long long pairTests = 0; double minPairMargin = 1e300;
     const int nonSector = (cfg->geometry == 0);
     const int nSect = nonSector ? 1 : 6;
 
@@ -154,6 +155,11 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
                         for (int j = 1; j < count; ++j) {
                             int rx0 = tx[i].idx, rx1 = tx[j].idx;
                             double low = tx[i].gain, high = tx[j].gain;
+                            if (rx0 != -1 && rx1 != -1) {
+                                double margin = fabs(10 * log(high) - 10 * log(low) - 15.);
+                                pairTests++;
+                                if (margin < minPairMargin) minPairMargin = margin;
+                            }
                             if (rx0 != -1 && rx1 != -1 && 10 * log(high) - 10 * log(low) > 15.) {
                                 pair += 2;
                                 tx[i].idx = -1; tx[j].idx = -1;
@@ -239,7 +245,7 @@ int oracle_run_n(const ref_config* cfg, ref_result* res, int* perUE, float* geom
         if (geom) ((double*)geom)[i] = u->channelGain;
     }
     res->simTimeMs = time; res->nSuccess = nSuccess; res->preambleTxSum = txSum; res->delaySum = delaySum;
-    res->captured = 1;
+    res->captured = 1; res->pairTests = pairTests; res->minPairMargin = minPairMargin;
     clock_gettime(CLOCK_MONOTONIC, &t1);
     res->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     free(c.ue); free(cnt); free(who); free(tx);

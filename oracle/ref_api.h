@@ -36,6 +36,11 @@ typedef struct ref_result {
     double seconds;
     /* restatement only: coverage of the rare Msg3-restart-lands-on-this-ms case */
     long long lateRestarts, lateAbsorbed;
+    /* restatement of NOMA.c only: the pairing test 10*log(high)-10*log(low) > 15. (N:276) is the one floating-point
+     * comparison that decides an integer outcome; pairTests = how many were evaluated, minPairMargin = the smallest
+     * |difference - 15| among them (how close any decision came to flipping under a different libm) */
+    long long pairTests;
+    double minPairMargin;
 } ref_result;
 
 /* perUE: nUE*16 ints in rach_gpu.h ra_sim_dump_ues order (may be NULL);

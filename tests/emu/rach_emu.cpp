@@ -124,7 +124,7 @@ static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, doubl
     pt.nUE = p.nUE; pt.P = p.nPreamble; pt.BI = p.backoffIndicator; pt.G = p.nGrantUL;
     pt.Wn = p.maxRarWindow; pt.M = p.maxMsg2TxCount; pt.A = p.accessTime;
     pt.maxTime = ra_horizon_ms(&p); pt.geometry = cfg->geometry ? 1 : 0; pt.R = ra_host_ring(&p);
-    pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed;
+    pt.nOcc = (pt.maxTime + pt.A - 1) / pt.A; pt.seed = p.seed; pt.cellRadius = p.cellRadius;
     ra_host_fill_point(&pt);
     std::vector<int> arrCum(pt.nOcc);
     ra_host_arrcum(&p, arrCum.data(), pt.nOcc);
@@ -150,7 +150,7 @@ static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, doubl
     for (int T = 0; T < pt.maxTime; ++T) {
         if (T % pt.A == 0) {
             for (int t = 0; t < NT; ++t) rn_phaseA0(job, s, T, t, NT);
-            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, i, p.cellRadius);
+            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, i);
             const unsigned nTx = s.bcount[(unsigned)T & Rm];
             for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseA2_item(pt, w, s, T, j);
             for (int sec = 0; sec < (pt.geometry ? RA_NSECT : 1); ++sec) rn_phaseB_sector(job, w, s, T, sec);

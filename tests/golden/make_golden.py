@@ -47,6 +47,12 @@ CASES = [
     ("w_p64_g16_bi10_20000", "w", dict(W, nUE=20000, nPreamble=64, nGrantUL=16, backoffIndicator=10, seed=4)),
     ("b_default_10000", "b", dict(B, nUE=10000, nGrantUL=54)),         # B as shipped
     ("b_g12_20000", "b", dict(B, nUE=20000, nGrantUL=12, seed=5)),
+    # README retx-50 table (README.md:110-113: -mrc 50 -> maxMsg2TxCount 49, W:134)
+    ("w_retx50_20000", "w", dict(W, nUE=20000, maxMsg2TxCount=49, seed=6)),
+    ("w_retx50_30000", "w", dict(W, nUE=30000, maxMsg2TxCount=49, seed=7)),
+    ("b_retx50_g12_20000", "b", dict(B, nUE=20000, nGrantUL=12, maxMsg2TxCount=49, seed=8)),
+    # the headline size, upper end of the reference's sweep (W:221); ~14 min of the reference's O(nUE) scans
+    ("w_default_100000", "w", dict(W, nUE=100000)),
 ]
 
 N_CASES = [
@@ -58,6 +64,8 @@ N_CASES = [
     ("n_retx3_r100_6000", dict(nUE=6000, maxMsg2TxCount=3, cellRadius=100.0, seed=5)),
     ("n_nonsector_8000", dict(nUE=8000, geometry=0, seed=6)),           # NOMA.c:325-447 switched in (N:688)
     ("n_nonsector_g12_20000", dict(nUE=20000, geometry=0, nGrantUL=12, seed=7)),   # with the commented nGrantUL = 12 (N:687)
+    ("n_default_50000", dict(nUE=50000, seed=8)),                      # BASELINE configs[3] size (N:648 sweep point)
+    ("n_default_100000", dict(nUE=100000, seed=9)),                    # upper end of NOMA.c's sweep
 ]
 
 U0_CASES = [
@@ -74,9 +82,22 @@ STAT_KEYS = ["simTimeMs", "nSuccess", "preambleTxSum", "delaySum", "failCountSum
 
 
 def main():
-    O.build(force=True)
+    """python make_golden.py                regenerate everything
+       python make_golden.py --only a,b,c   run only those cases and merge them into the committed files"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
+    O.build(force=only is None)
     stats, ues = {}, {}
+    if only is not None:
+        with open(os.path.join(here, "golden_stats.json")) as f:
+            stats = json.load(f)
+        ues = dict(np.load(os.path.join(here, "golden_ues.npz")))
+    sel = lambda name: only is None or name in only
     for name, variant, kw in CASES:
+        if not sel(name):
+            continue
         cfg = O.make_config(**kw)
         res, ue, geom = O.run_ref(variant, cfg, per_ue=True, geom=(variant == "w"))
         d = res.as_dict()
@@ -90,6 +111,8 @@ def main():
             ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
         print("%-28s %s" % (name, {k: d[k] for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum")}))
     for name, kw in N_CASES:
+        if not sel(name):
+            continue
         cfg = O.make_config_n(**kw)
         res, ue, gain = O.run_ref_n(cfg)
         full = dict(O.DEFAULTS); full.update(O.N_DEFAULTS); full.update(kw)
@@ -102,6 +125,8 @@ def main():
             ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
         print("%-28s %s" % (name, stats[name]["stats"]))
     for name, kw in U0_CASES:
+        if not sel(name):
+            continue
         cfg = O.make_config_u0(**kw)
         res, ue = O.run_ref_u0(cfg)
         full = dict(O.DEFAULTS); full.update(O.U0_DEFAULTS); full.update(kw)
@@ -113,7 +138,6 @@ def main():
         if cfg.nUE <= 3000:
             ues[name] = ue.astype(np.int16) if np.abs(ue).max() < 32768 else ue
         print("%-28s %s dropped %d" % (name, stats[name]["stats"], stats[name]["dropped"]))
-    here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "golden_stats.json"), "w") as f:
         json.dump(stats, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(here, "golden_ues.npz"), **ues)

@@ -102,3 +102,32 @@ def test_beta_schedule_equals_the_c_expression_for_many_sizes(pkg, oracle):
             at_ref = lib.oracle_beta_arrivals(n, a, ref.ctypes.data_as(C.c_void_p))
             arr, at = pkg.arrival_schedule(pkg.default_params(nUE=n, accessTime=a))
             assert at == at_ref and np.array_equal(arr, ref), (n, a)
+
+
+def test_validation_without_a_device(pkg):
+    """ra_params_validate = the checks of ra_sim_create.  Variant N: the rejection loops of activeUE
+    (NOMA.c:167-172 r > 35 m, NOMA.c:185-189 gain >= 1e-7) never end for a radius at or below 35 m (e.g. a
+    zero-initialised ra_params) and practically never beyond a few km -- refused instead of hanging the GPU."""
+    ok = pkg.default_params(variant=2)
+    assert pkg.validate_params(ok) == (0, "")
+    for bad in (0.0, 35.0, -1.0, float("nan"), float("inf"), 5001.0):
+        rc, msg = pkg.validate_params(pkg.default_params(variant=2, cellRadius=bad))
+        assert rc == -1 and "cellRadius" in msg, bad
+    assert pkg.validate_params(pkg.default_params(variant=2, cellRadius=35.5))[0] == 0
+    # W never feeds the radius back into the dynamics (W:392-415 are side outputs): any value is accepted there
+    assert pkg.validate_params(pkg.default_params(cellRadius=0.0))[0] == 0
+    rc, msg = pkg.validate_params(pkg.default_params(nPreamble=0))
+    assert rc == -1 and "nPreamble" in msg
+
+
+@pytest.mark.parametrize("a", [5, 64, 4096])
+def test_beta_schedule_beyond_the_reference_horizon_is_monotone(pkg, a):
+    """maxTimeMs above the reference's 10 s: beta_dist's (1-x)^3 is negative for x > 1 (W:844-847); nobody
+    arrives there, the cumulative schedule never decreases and never exceeds nUE."""
+    p = pkg.default_params(nUE=100000, accessTime=a)
+    p.maxTimeMs = 30000
+    arr, at = pkg.arrival_schedule(p)
+    assert len(arr) == 30000 and (arr >= 0).all() and arr.sum() <= 100000
+    assert arr[10000:].sum() == 0 or a == 5      # with the default subframe everybody has arrived by 7970 ms
+    ref, _ = pkg.arrival_schedule(pkg.default_params(nUE=100000, accessTime=a))
+    assert np.array_equal(arr[:10000], ref)

@@ -39,8 +39,6 @@ def test_restatement_matches_reference_fixture(oracle, golden, name):
         assert hashlib.sha256(np.ascontiguousarray(gain).tobytes()).hexdigest() == g["gain_sha256"]
         assert int((ue[:, 15] > 0).sum()) == g["dropped"]
         return
-    if g["config"]["nUE"] > 20000:
-        pytest.skip("covered by the slow suite / GPU box")
     cfg = oracle.make_config(**g["config"])
     res, ue, geom = oracle.run_port(cfg, per_ue=True, geom=True)
     d = res.as_dict()
