@@ -38,8 +38,10 @@
 
 #ifdef __CUDACC__
 #define RA_HD __host__ __device__ __forceinline__
+#define RA_HDM __host__ __device__ __forceinline__      /* member functions */
 #else
 #define RA_HD static inline
+#define RA_HDM inline
 struct uint4 { unsigned x, y, z, w; };
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = {a, b, c, d}; return r; }
 #endif
@@ -80,6 +82,18 @@ template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) 
 #define RA_AMIN(p, v)   ra_emu_min((p), (v))
 #endif
 
+/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1
+ * (0xFFFFFFFF for d==1).  floor(x*magic/2^32) is q or q+1 for d >= 2 (error < x/2^32 < 1/2)
+ * and x-1 for d == 1, so two conditional corrections make the remainder exact. */
+RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ull / d) + 1u; }
+RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic) {
+    unsigned q = rach_mulhi32(x, magic);
+    int r = (int)(x - q * d);
+    if (r < 0) r += (int)d;
+    if (r >= (int)d) r -= (int)d;
+    return (unsigned)r;
+}
+
 /* ---- one parameter point, device view ---------------------------------------------------- */
 struct RaPointDev {
     int nUE, P, BI, G, Wn, M, A, maxTime;
@@ -92,7 +106,66 @@ struct RaPointDev {
      * here so that a launch whose replications share one point reads them as kernel constants */
     unsigned oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore, oExtraFirst, oClsSize;
     unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes;
+    /* rand() % backoffIndicator (W:514,540,685), rand() % nPreamble (W:478,502,701), subTime % accessTime (W:518) */
+    RA_HDM unsigned modBI(unsigned x) const { return ra_mod(x, (unsigned)BI, magicBI); }
+    RA_HDM unsigned modP(unsigned x) const { return ra_mod(x, (unsigned)P, magicP); }
+    RA_HDM unsigned modA(unsigned x) const { return ra_mod(x, (unsigned)A, magicA); }
 };
+
+/* table layout for (R, P); 16-byte records first.  One definition for the runtime point (ra_layout) and for the
+ * compile-time view below. */
+struct RaLayout {
+    unsigned oSLand, oSUnc, oSLandMeta, oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore,
+             oExtraFirst, oClsSize, oHist, oSIdx, smemBytes;
+};
+#define RA_LAYOUT_BODY(R_, P_) \
+    RaLayout l = {}; unsigned o = 0; const unsigned RP = (unsigned)(R_) * (unsigned)(P_), P4 = 4u * (unsigned)(P_); \
+    l.oSLand = o;      o += 16u * RA_LCAP; \
+    l.oSUnc = o;       o += 16u * RA_UCAP; \
+    l.oSLandMeta = o;  o += 4u * RA_LCAP; \
+    l.oMinI = o;       o += 4u * RP; \
+    l.oCnt = o;        o += 4u * RP; \
+    l.oBcount = o;     o += 4u * (unsigned)(R_); \
+    l.oM3count = o;    o += 4u * RA_M3RING; \
+    l.oN = o;          o += P4; \
+    l.oL1 = o;         o += P4; \
+    l.oNlList = o;     o += P4; \
+    l.oL1m = o;        o += P4; \
+    l.oL2 = o;         o += P4; \
+    l.oBefore = o;     o += P4; \
+    l.oExtraFirst = o; o += P4; \
+    l.oClsSize = o;    o += P4; \
+    l.oHist = o;       o += 4u * RA_HBINS; \
+    l.oSIdx = o;       o += 4u * RA_SCAP; \
+    l.smemBytes = o; \
+    return l;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr RaLayout ra_layout_of(int R, int P) { RA_LAYOUT_BODY(R, P) }
+
+/* Compile-time view of a point of the family (P, BI, A, Wn): every reference default that the step's inner loops
+ * divide by or index with (W:71-72,76,78: 54 preambles, BI 20, maxRarWindow 6, accessTime 5) becomes an immediate --
+ * `% BI`, `% P`, `% A` turn into multiply-shift sequences without corrections, table offsets into immediates, and the
+ * dozen shared-memory loads of these values per event disappear.  Same layout as RaPointDev (no data members
+ * added): the kernel casts its shared-memory copy of the point.  nUE, G, M, horizon, seed ... stay runtime values. */
+template <int P_, int BI_, int A_, int Wn_, int R_>
+struct RaPointFixed : RaPointDev {
+    static constexpr int P = P_, BI = BI_, A = A_, Wn = Wn_, R = R_;
+    static constexpr RaLayout L = ra_layout_of(R_, P_);
+    static constexpr unsigned oSLand = L.oSLand, oSUnc = L.oSUnc, oSLandMeta = L.oSLandMeta, oMinI = L.oMinI, oCnt = L.oCnt,
+        oBcount = L.oBcount, oM3count = L.oM3count, oN = L.oN, oL1 = L.oL1, oNlList = L.oNlList, oL1m = L.oL1m, oL2 = L.oL2,
+        oBefore = L.oBefore, oExtraFirst = L.oExtraFirst, oClsSize = L.oClsSize, oHist = L.oHist, oSIdx = L.oSIdx,
+        smemBytes = L.smemBytes;
+    RA_HDM unsigned modBI(unsigned x) const { return x % (unsigned)BI_; }
+    RA_HDM unsigned modP(unsigned x) const { return x % (unsigned)P_; }
+    RA_HDM unsigned modA(unsigned x) const { return x % (unsigned)A_; }
+};
+/* the reference's defaults (RandomAccessWithNOMA.c:71-78); ring = next_pow2(BI + max(A,5) + Wn) = 32 */
+typedef RaPointFixed<54, 20, 5, 6, 32> RaPointDef;
+RA_HD bool ra_point_is_default_family(const RaPointDev& pt) {
+    return pt.P == RaPointDef::P && pt.BI == RaPointDef::BI && pt.A == RaPointDef::A && pt.Wn == RaPointDef::Wn && pt.R == RaPointDef::R;
+}
 
 /* ---- per-CTA global workspace ------------------------------------------------------------ */
 struct RaWork {
@@ -123,11 +196,13 @@ struct RaShared {
 /* per-thread counters, folded into RaShared at the end of the replication */
 struct RaAcc { unsigned contFailed, collP, txop, collScans, totScans; };
 
-struct RaJob {
-    const RaPointDev* pt;
+template <class PT>
+struct RaJobT {
+    const PT* pt;             /* RaPointDev, or a compile-time view of it (RaPointDef)      */
     unsigned rep;             /* tape replication id                                        */
     int* dump;                /* [nUE][16] or NULL                                          */
 };
+typedef RaJobT<RaPointDev> RaJob;
 
 /* ---- record packing ---------------------------------------------------------------------- */
 /* x: idx   y: txTime   z: timerStart | failCount<<16   w: preamble | mrc<<8 | ptc<<16 | flag<<31
@@ -143,18 +218,6 @@ RA_HD unsigned ra_rec_ts(const uint4& r)   { return r.z & 0xFFFFu; }
 RA_HD unsigned ra_rec_fail(const uint4& r) { return r.z >> 16; }
 RA_HD unsigned ra_z(unsigned ts, unsigned fail) { return (ts & 0xFFFFu) | (fail << 16); }
 
-/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1
- * (0xFFFFFFFF for d==1).  floor(x*magic/2^32) is q or q+1 for d >= 2 (error < x/2^32 < 1/2)
- * and x-1 for d == 1, so two conditional corrections make the remainder exact. */
-RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ull / d) + 1u; }
-RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic) {
-    unsigned q = rach_mulhi32(x, magic);
-    int r = (int)(x - q * d);
-    if (r < 0) r += (int)d;
-    if (r >= (int)d) r -= (int)d;
-    return (unsigned)r;
-}
-
 /* slot alignment, W:518-527 (= W:544-553, W:688-697) */
 RA_HD int ra_align(int subTime, int A, unsigned magicA) {
     int r = (int)ra_mod((unsigned)subTime, (unsigned)A, magicA);
@@ -163,7 +226,16 @@ RA_HD int ra_align(int subTime, int A, unsigned magicA) {
     return subTime + (A - r + 1);
 }
 
-RA_HD rach_u32x4 ra_draws(const RaJob& job, unsigned ue, int ms) {
+template <class PT>
+RA_HD int ra_align_pt(const PT& pt, int subTime) {
+    const int r = (int)pt.modA((unsigned)subTime);
+    if (r == 0) return subTime + 1;
+    if (r == 1) return subTime;
+    return subTime + (pt.A - r + 1);
+}
+
+template <class PT>
+RA_HD rach_u32x4 ra_draws(const RaJobT<PT>& job, unsigned ue, int ms) {
     return rach_tape_block(job.pt->seed, job.rep, ue, (unsigned)ms, 0u, RACH_TAPE_TAG_UE);
 }
 
@@ -202,31 +274,16 @@ struct RaTabsT { unsigned *minI, *cnt, *bcount, *m3count, *N, *l1, *nlList, *l1m
 #define S_sLandMeta  RA_T(sLandMeta, oSLandMeta)   /* [RA_LCAP]                                                   */
 #define S_sUnc       RA_T(sUnc, oSUnc)             /* [RA_UCAP]  first uncertain movers of the ms                 */
 
-/* table layout for (R, P); 16-byte records first */
 RA_HD void ra_layout(RaPointDev& pt) {
-    const unsigned RP = (unsigned)pt.R * (unsigned)pt.P, P = (unsigned)pt.P;
-    unsigned o = 0;
-    pt.oSLand = o;      o += 16u * RA_LCAP;
-    pt.oSUnc = o;       o += 16u * RA_UCAP;
-    pt.oSLandMeta = o;  o += 4u * RA_LCAP;
-    pt.oMinI = o;       o += 4u * RP;
-    pt.oCnt = o;        o += 4u * RP;
-    pt.oBcount = o;     o += 4u * (unsigned)pt.R;
-    pt.oM3count = o;    o += 4u * RA_M3RING;
-    pt.oN = o;          o += 4u * P;
-    pt.oL1 = o;         o += 4u * P;
-    pt.oNlList = o;     o += 4u * P;
-    pt.oL1m = o;        o += 4u * P;
-    pt.oL2 = o;         o += 4u * P;
-    pt.oBefore = o;     o += 4u * P;
-    pt.oExtraFirst = o; o += 4u * P;
-    pt.oClsSize = o;    o += 4u * P;
-    pt.oHist = o;       o += 4u * RA_HBINS;
-    pt.oSIdx = o;       o += 4u * RA_SCAP;
-    pt.smemBytes = o;
+    const RaLayout l = ra_layout_of(pt.R, pt.P);
+    pt.oSLand = l.oSLand; pt.oSUnc = l.oSUnc; pt.oSLandMeta = l.oSLandMeta; pt.oMinI = l.oMinI; pt.oCnt = l.oCnt;
+    pt.oBcount = l.oBcount; pt.oM3count = l.oM3count; pt.oN = l.oN; pt.oL1 = l.oL1; pt.oNlList = l.oNlList;
+    pt.oL1m = l.oL1m; pt.oL2 = l.oL2; pt.oBefore = l.oBefore; pt.oExtraFirst = l.oExtraFirst; pt.oClsSize = l.oClsSize;
+    pt.oHist = l.oHist; pt.oSIdx = l.oSIdx; pt.smemBytes = l.smemBytes;
 }
 
-RA_HD unsigned ra_first_scan(const RaPointDev& pt, unsigned p) {     /* s[p] of the header comment */
+template <class PT>
+RA_HD unsigned ra_first_scan(const PT& pt, unsigned p) {     /* s[p] of the header comment */
     unsigned a = S_l1[p], b = S_l2[p];
     return a < b ? a : b;
 }
@@ -234,15 +291,22 @@ RA_HD unsigned ra_first_scan(const RaPointDev& pt, unsigned p) {     /* s[p] of 
 /* per-ms work lists: the first entries live in shared memory (the small phases then never wait for
  * L2), the overflow in the block's global workspace */
 /* (x + 1 <= cap instead of x < cap: no "pointless comparison" diagnostics when a capacity is 0) */
-RA_HD uint4 ra_lrec_get(const RaPointDev& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLand[l] : w.landerRec[l]; }
-RA_HD unsigned ra_lmeta_get(const RaPointDev& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLandMeta[l] : w.landerMeta[l]; }
-RA_HD void ra_lmeta_set(const RaPointDev& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) S_sLandMeta[l] = v; else w.landerMeta[l] = v; }
-RA_HD void ra_lmeta_add(const RaPointDev& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) RA_AADD(&S_sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
-RA_HD void ra_unc_set(const RaPointDev& pt, const RaWork& w, unsigned u, const uint4& e) { if (u + 1 <= RA_UCAP) S_sUnc[u] = e; else w.uncertain[u] = e; }
-RA_HD uint4 ra_unc_get(const RaPointDev& pt, const RaWork& w, unsigned u) { return u + 1 <= RA_UCAP ? S_sUnc[u] : w.uncertain[u]; }
+template <class PT>
+RA_HD uint4 ra_lrec_get(const PT& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLand[l] : w.landerRec[l]; }
+template <class PT>
+RA_HD unsigned ra_lmeta_get(const PT& pt, const RaWork& w, unsigned l) { return l + 1 <= RA_LCAP ? S_sLandMeta[l] : w.landerMeta[l]; }
+template <class PT>
+RA_HD void ra_lmeta_set(const PT& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) S_sLandMeta[l] = v; else w.landerMeta[l] = v; }
+template <class PT>
+RA_HD void ra_lmeta_add(const PT& pt, const RaWork& w, unsigned l, unsigned v) { if (l + 1 <= RA_LCAP) RA_AADD(&S_sLandMeta[l], v); else RA_AADD(&w.landerMeta[l], v); }
+template <class PT>
+RA_HD void ra_unc_set(const PT& pt, const RaWork& w, unsigned u, const uint4& e) { if (u + 1 <= RA_UCAP) S_sUnc[u] = e; else w.uncertain[u] = e; }
+template <class PT>
+RA_HD uint4 ra_unc_get(const PT& pt, const RaWork& w, unsigned u) { return u + 1 <= RA_UCAP ? S_sUnc[u] : w.uncertain[u]; }
 
 /* append a record to move bucket `m`; returns its position */
-RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
+template <class PT>
+RA_HD unsigned ra_bucket_push(const PT& pt, const RaWork& w, RaShared& s, int m, const uint4& rec) {
     unsigned slot = (unsigned)m & (unsigned)(pt.R - 1);
     /* one shared-memory atomic per record: measured 8 % faster on B200 than aggregating the lanes of a warp
      * per bucket with __match_any_sync (the variable-mask shuffle that follows costs more than the contention) */
@@ -254,7 +318,8 @@ RA_HD unsigned ra_bucket_push(const RaPointDev& pt, const RaWork& w, RaShared& s
 
 /* a UE (re)enters the Msg1 phase with transmission time X = rec.y > now: visible from X on,
  * its RAR window expires at X + Wn - 1 (rarWindow is 1 at X, W:493) */
-RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec) {
+template <class PT>
+RA_HD void ra_schedule(const PT& pt, const RaWork& w, RaShared& s, const uint4& rec) {
     int m = (int)rec.y + pt.Wn - 1;
     const unsigned pos = ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
@@ -267,19 +332,22 @@ RA_HD void ra_schedule(const RaPointDev& pt, const RaWork& w, RaShared& s, const
 /* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old
  * txTime, or a Msg3 restart landing on `now`, W:693): invisible to scans, rarWindow counts
  * from 0 at `now`, so it expires at now + Wn */
-RA_HD void ra_park_stale(const RaPointDev& pt, const RaWork& w, RaShared& s, int now, uint4 rec) {
+template <class PT>
+RA_HD void ra_park_stale(const PT& pt, const RaWork& w, RaShared& s, int now, uint4 rec) {
     rec.w |= 0x80000000u;
     ra_bucket_push(pt, w, s, now + pt.Wn, rec);
 }
 
-RA_HD void ra_msg3_push(const RaPointDev& pt, const RaWork& w, RaShared& s, int due, const uint4& rec) {
+template <class PT>
+RA_HD void ra_msg3_push(const PT& pt, const RaWork& w, RaShared& s, int due, const uint4& rec) {
     unsigned slot = (unsigned)due & (RA_M3RING - 1);
     unsigned pos = RA_AADD(&S_m3count[slot], 1u);
     if (pos >= (unsigned)w.cap3) { s.overflow = 1; return; }
     w.msg3[(size_t)slot * w.cap3 + pos] = rec;
 }
 
-RA_HD void ra_lander_push(const RaPointDev& pt, const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
+template <class PT>
+RA_HD void ra_lander_push(const PT& pt, const RaWork& w, RaShared& s, const uint4& rec, unsigned member) {
     unsigned l = RA_AADD(&s.nLanders, 1u);
     if (l >= (unsigned)w.cap) { s.overflow = 1; return; }
     if (l + 1 <= RA_LCAP) { S_sLand[l] = rec; S_sLandMeta[l] = member; }
@@ -307,9 +375,9 @@ RA_HD int ra_sector(int r31) {
 /* =========================================================================================
  * Job start: empty calendars and cohort tables (calloc + initialUE, W:229-234).
  * ========================================================================================= */
-template <bool DUMP>
-RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_job_init(const RaJobT<PT>& job, RaShared& s, int tid, int nt) {
+    const PT& pt = *job.pt;
     for (int i = tid; i < pt.R * pt.P; i += nt) { S_cnt[i] = 0; S_minI[i] = RA_INF32; }
     for (int i = tid; i < pt.R; i += nt) S_bcount[i] = 0;
     for (int i = tid; i < RA_M3RING; i += nt) S_m3count[i] = 0;
@@ -327,8 +395,9 @@ RA_HD void ra_job_init(const RaJob& job, RaShared& s, int tid, int nt) {
  * Phase 0 -- start of ms T: grant reset (W:268-269), arrival gate (W:276-292), per-class
  * view of the visible cohorts.
  * ========================================================================================= */
-RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
-    const RaPointDev& pt = *job.pt;
+template <class PT>
+RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt) {
+    const PT& pt = *job.pt;
     const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1);
     for (int p = tid; p < P; p += nt) {
@@ -363,19 +432,19 @@ RA_HD void ra_phase0(const RaJob& job, RaShared& s, int T, int tid, int nt) {
  *   [nMov, +nArr)        arrivals: activateUEs + first selectPreamble, W:294-298,383-394,477-487
  *   [.., +nM3)           Msg3 due: requestResourceAllocation, W:667-710
  * ========================================================================================= */
-template <bool DUMP>
-RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d);
+template <bool DUMP, class PT>
+RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d);
 
-template <bool DUMP>
-RA_HD void ra_phase1_mover(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec) {
+template <bool DUMP, class PT>
+RA_HD void ra_phase1_mover(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec) {
     if (rec.x == RA_DEAD) return;
     ra_phase1_mover_d<DUMP>(job, w, s, acc, T, item, rec, ra_draws(job, rec.x, T));
 }
 
 /* the draws of (UE, T) are passed in so that the kernel can run two Philox chains side by side */
-template <bool DUMP>
-RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d) {
+    const PT& pt = *job.pt;
     if (rec.x == RA_DEAD) return;
     const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
     unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
@@ -383,14 +452,14 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     const bool uncertain = !stale && idx < S_l1[p0];
     const bool limit = (int)mrc >= pt.M;
     /* both branches draw the backoff: retry W:540 (1st draw), limit W:514 (2nd draw) */
-    const int tmp = (int)ra_mod((limit ? d.v[1] : d.v[0]) >> 1, (unsigned)pt.BI, pt.magicBI);
+    const int tmp = (int)pt.modBI((limit ? d.v[1] : d.v[0]) >> 1);
     /* Both branches written as selects: one mover in ten takes the limit branch, so almost every warp would
      * otherwise execute both sides of an if/else.
      *   retry branch, W:532-558: subTime = time + tmp (W:542); maxRarCounter++, preambleTxCounter++
      *   limit branch, W:498-531: new preamble, counters reset, timer = 0, failCount++, subTime = CURRENT
      *     txTime + tmp (W:516): an old txTime if stale, T+1 if a lower index postponed me (certain above the
      *     leader), T under the not-postponed hypothesis if uncertain (settled in phase 3) */
-    const unsigned pl = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
+    const unsigned pl = pt.modP(d.v[0] >> 1);
     const unsigned pnew = limit ? pl : p0;
     const unsigned fail = ra_rec_fail(rec) + (limit ? 1u : 0u);
     const unsigned z = limit ? ra_z((unsigned)T, fail) : rec.z;
@@ -399,7 +468,7 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     acc.contFailed += limit ? 1u : 0u;
     const int base = limit ? (stale ? (int)rec.y : (uncertain ? T : T + 1)) : T;
     if (fail > 0xFFFFu || ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
-    const int X = ra_align(base + tmp, pt.A, pt.magicA);
+    const int X = ra_align_pt(pt, base + tmp);
     const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
     if (uncertain) {
         unsigned u = RA_AADD(&s.nUnc, 1u);
@@ -420,9 +489,9 @@ RA_HD void ra_phase1_mover_d(const RaJob& job, const RaWork& w, RaShared& s, RaA
     }
 }
 
-template <bool DUMP>
-RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_phase1_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
+    const PT& pt = *job.pt;
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < s.nMov) {
         ra_phase1_mover<DUMP>(job, w, s, acc, T, item, w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item]);
@@ -433,7 +502,7 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         /* ---------------- arrival, W:383-394 + first draw W:477-487 ---------------- */
         unsigned idx = (unsigned)s.acOld + item;
         rach_u32x4 d = ra_draws(job, idx, T);
-        unsigned p = ra_mod(d.v[pt.geometry ? 2 : 0] >> 1, (unsigned)pt.P, pt.magicP);
+        unsigned p = pt.modP(d.v[pt.geometry ? 2 : 0] >> 1);
         uint4 nr = make_uint4(idx, (unsigned)(T + 1), ra_z((unsigned)T, 0), ra_w3(p, 0, 1, 0));
         if (DUMP) {
             int* row = job.dump + (size_t)idx * RA_DUMP_W;
@@ -469,9 +538,9 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
         } else {
             /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
             acc.contFailed++;
-            int tmp = (int)ra_mod(d.v[0] >> 1, (unsigned)pt.BI, pt.magicBI);
+            int tmp = (int)pt.modBI(d.v[0] >> 1);
             int X = ra_align(T + tmp, 5, RA_MAGIC5);
-            unsigned pnew = ra_mod(d.v[1] >> 1, (unsigned)pt.P, pt.magicP);
+            unsigned pnew = pt.modP(d.v[1] >> 1);
             unsigned fail = ra_rec_fail(rec) + 1;
             if (fail > 0xFFFFu) s.overflow = 2;
             uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, ra_rec_ptc(rec), 0));
@@ -490,7 +559,8 @@ RA_HD void ra_phase1_item(const RaJob& job, const RaWork& w, RaShared& s, RaAcc&
  * nobody has postponed them: decide in index order (a landing is itself a scan of its new
  * class and postpones the members above it).
  * ========================================================================================= */
-RA_HD void ra_phase2_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) {
+template <class PT>
+RA_HD void ra_phase2_serial(const PT& pt, const RaWork& w, RaShared& s) {
     const unsigned n = s.nC3;
     for (unsigned i = 0; i < n; ++i) {                      /* selection by ascending idx */
         unsigned best = i;
@@ -507,9 +577,9 @@ RA_HD void ra_phase2_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) 
 /* =========================================================================================
  * Phase 3 -- movers below the natural leader of their class, now that s[] is final.
  * ========================================================================================= */
-template <bool DUMP>
-RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned u) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_phase3_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, unsigned u) {
+    const PT& pt = *job.pt;
     const uint4 e = ra_unc_get(pt, w, u);
     const unsigned idx = e.y, p0 = e.z & 0xFFu;
     const unsigned sp = ra_first_scan(pt, p0);
@@ -518,10 +588,10 @@ RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
     /* limit branch, W:498-531 */
     uint4 rec = w.bucket[(size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap + e.x];
     rach_u32x4 d = ra_draws(job, idx, T);
-    unsigned pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
-    int tmp = (int)ra_mod(d.v[1] >> 1, (unsigned)pt.BI, pt.magicBI);
+    unsigned pnew = pt.modP(d.v[0] >> 1);
+    int tmp = (int)pt.modBI(d.v[1] >> 1);
     int base = T + (idx > sp ? 1 : 0);                      /* postponed by the first scan, W:658 */
-    int X = ra_align(base + tmp, pt.A, pt.magicA);
+    int X = ra_align_pt(pt, base + tmp);
     uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, ra_rec_fail(rec) + 1), ra_w3(pnew, 0, 1, 0));
     if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + 3] = T + 1;
     if (X == T) ra_lander_push(pt, w, s, nr, pnew == p0 ? 1u : 0u);   /* S_l2 already holds it (phase 2) */
@@ -532,7 +602,8 @@ RA_HD void ra_phase3_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
  * Phase 3b (only if nE1 > 0) -- a Msg3 restart that landed on T at index k is counted by the
  * first scan of its class at an index above k (W:613-621), which postpones it.
  * ========================================================================================= */
-RA_HD void ra_phase3b_item(const RaPointDev& pt, const RaWork& w, RaShared& s, unsigned e) {
+template <class PT>
+RA_HD void ra_phase3b_item(const PT& pt, const RaWork& w, RaShared& s, unsigned e) {
     const uint4 r = w.e1Rec[e];
     const unsigned k = r.x, q = ra_rec_p(r);
     unsigned bestIdx = RA_INF32, bestRef = RA_INF32;
@@ -553,7 +624,8 @@ RA_HD void ra_phase3b_item(const RaPointDev& pt, const RaWork& w, RaShared& s, u
  *   class items  [0, P):        first scan by the natural leader (a visible non-mover)
  *   lander items [P, P+nLanders): scan by a UE that re-transmits in this ms
  * ========================================================================================= */
-RA_HD void ra_single_push(const RaPointDev& pt, const RaWork& w, RaShared& s, unsigned idx) {
+template <class PT>
+RA_HD void ra_single_push(const PT& pt, const RaWork& w, RaShared& s, unsigned idx) {
     unsigned k = RA_AADD(&s.nSingles, 1u);
     if (k < RA_SCAP) S_sIdx[k] = idx;
     w.singles[k] = idx;
@@ -566,7 +638,8 @@ RA_HD void ra_count_scan(RaAcc& acc, unsigned size) {
     else { acc.collP += size; acc.txop += size; acc.collScans++; }   /* W:650-652, B:349 */
 }
 
-RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
+template <class PT>
+RA_HD void ra_phase4_item(const PT& pt, const RaWork& w, RaShared& s, RaAcc& acc, unsigned item) {
     if (item < (unsigned)pt.P) {
         const unsigned q = item;
         const unsigned sq = ra_first_scan(pt, q);
@@ -599,7 +672,8 @@ RA_HD void ra_phase4_item(const RaPointDev& pt, const RaWork& w, RaShared& s, Ra
  * index order are granted (strict '<' after the increment, W:639-641).
  * tau = highest granted index (RA_INF32: all, 0 with nobody granted handled by flag).
  * ========================================================================================= */
-RA_HD void ra_phase5_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) {
+template <class PT>
+RA_HD void ra_phase5_serial(const PT& pt, const RaWork& w, RaShared& s) {
     const unsigned n = s.nSingles;
     long long K = (long long)pt.G - 1 - s.grantCheck;
     if (K < 0) K = 0;
@@ -623,7 +697,8 @@ RA_HD void ra_phase5_serial(const RaPointDev& pt, const RaWork& w, RaShared& s) 
 #ifdef __CUDACC__
 /* the same threshold computed by one warp: histogram over index bins (filled by phase 4) ->
  * the bin holding the K-th smallest -> exact rank inside that bin */
-__device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWork& w, RaShared& s, int lane) {
+template <class PT>
+__device__ __forceinline__ void ra_phase5_warp(const PT& pt, const RaWork& w, RaShared& s, int lane) {
     const unsigned n = s.nSingles;
     long long K = (long long)pt.G - 1 - s.grantCheck;
     if (K < 0) K = 0;
@@ -669,9 +744,9 @@ __device__ __forceinline__ void ra_phase5_warp(const RaPointDev& pt, const RaWor
 RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && idx <= s.tau; }
 
 /* a granted visible non-mover leaves its bucket and cohort and queues Msg3 (W:642-645) */
-template <bool DUMP>
-RA_HD void ra_grant_nonmover(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned q, unsigned slot, size_t at) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_grant_nonmover(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, unsigned q, unsigned slot, size_t at) {
+    const PT& pt = *job.pt;
     uint4 rec = w.bucket[at];
     w.bucket[at].x = RA_DEAD;
     S_cnt[slot * pt.P + q] -= 1; S_minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
@@ -687,9 +762,9 @@ RA_HD void ra_grant_nonmover(const RaJob& job, const RaWork& w, RaShared& s, int
  * Phase 6 -- apply the outcomes of the scans (W:641-648, W:653-661), retire ms T.
  * items: [0,P) classes, [P, P+nLanders) landers, [.., +nE1) late restarts
  * ========================================================================================= */
-template <bool DUMP>
-RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T, unsigned item) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_phase6_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, unsigned item) {
+    const PT& pt = *job.pt;
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < (unsigned)pt.P) {
         const unsigned q = item;
@@ -735,9 +810,9 @@ RA_HD void ra_phase6_item(const RaJob& job, const RaWork& w, RaShared& s, int T,
 /* Phase 6b (every thread, only if nNl > 0) -- fallback for a granted visible non-mover whose position hint
  * was stale (two UEs lowered the cohort minimum at the same time): find the record in the bucket of its move
  * time by index. */
-template <bool DUMP>
-RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
-    const RaPointDev& pt = *job.pt;
+template <bool DUMP, class PT>
+RA_HD void ra_phase6b(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
+    const PT& pt = *job.pt;
     for (unsigned e = 0; e < s.nNl; ++e) {
         const unsigned q = S_nlList[e], slot = S_l1m[q], want = S_l1[q];
         const unsigned n = S_bcount[slot];
@@ -750,14 +825,16 @@ RA_HD void ra_phase6b(const RaJob& job, const RaWork& w, RaShared& s, int T, int
 }
 
 /* with phase 6 (every thread), only if the ms had singleton scans */
-RA_HD void ra_hist_clear(const RaPointDev& pt, const RaWork& w, RaShared& s, int tid, int nt) {
+template <class PT>
+RA_HD void ra_hist_clear(const PT& pt, const RaWork& w, RaShared& s, int tid, int nt) {
     const unsigned n = s.nSingles;
     if (n > RA_HBINS / 2) { for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0; }
     else for (unsigned j = tid; j < n; j += nt) S_hist[(j < RA_SCAP ? S_sIdx[j] : w.singles[j]) >> pt.hshift] = 0;
 }
 
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */
-RA_HD bool ra_ms_done(const RaPointDev& pt, const RaShared& s, int T, int* simTime) {
+template <class PT>
+RA_HD bool ra_ms_done(const PT& pt, const RaShared& s, int T, int* simTime) {
     if (s.nSuccess == (unsigned)pt.nUE) { *simTime = T; return true; }
     if (T + 1 >= pt.maxTime) { *simTime = pt.maxTime; return true; }
     return false;
@@ -767,8 +844,9 @@ RA_HD bool ra_ms_done(const RaPointDev& pt, const RaShared& s, int T, int* simTi
  * End of the replication (DUMP only): state of the UEs still in flight after the last
  * executed ms `last`, as the reference's per-ms bookkeeping would have left it.
  * ========================================================================================= */
-RA_HD void ra_dump_inflight(const RaJob& job, const RaWork& w, RaShared& s, int last, int tid, int nt) {
-    const RaPointDev& pt = *job.pt;
+template <class PT>
+RA_HD void ra_dump_inflight(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int last, int tid, int nt) {
+    const PT& pt = *job.pt;
     for (int slot = 0; slot < pt.R; ++slot) {
         /* absolute move time of this slot: the value in (last, last+R] congruent to slot */
         int m = last + 1 + (int)(((unsigned)slot - (unsigned)(last + 1)) & (unsigned)(pt.R - 1));

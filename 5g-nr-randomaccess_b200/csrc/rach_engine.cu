@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -41,6 +42,10 @@
 #endif
 #define RA_NT_BIG 256
 #define RA_MINB_BIG 5
+/* few replications per device (strong scaling, small sweeps): one replication cannot be split over blocks, so the block
+ * grows instead -- 512 threads x 2 per SM (64 registers) when there are at most two replications per SM */
+#define RA_NT_HUGE 512
+#define RA_MINB_HUGE 2
 #ifndef RA_NT_N
 #define RA_NT_N 192        /* variant N: phase B runs one warp leader per sector, 6 warps = 6 sectors.  Measured */
 #define RA_MINB_N 5        /* (50k UEs x 2048 replications): 192 x 5 169 ms, 128 x 8 174 ms, 256 x 4 203 ms    */
@@ -69,8 +74,11 @@ struct RaKernelArgs {
     int               nJobs, maxP, maxR;
 };
 
-template <bool DUMP, int NT, int MINB>
+template <bool DUMP, int NT, int MINB, bool FIXED>
 __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
+    /* FIXED: every point of the launch belongs to the reference's default family (54 preambles, BI 20, subframe 5, RAR
+     * window 5): those values are immediates in this instantiation (RaPointDef); otherwise they are read from the point */
+    typedef typename std::conditional<FIXED, RaPointDef, RaPointDev>::type PT;
     __shared__ RaShared s;
     __shared__ RaPointDev sPt;
     __shared__ int sJob;
@@ -91,8 +99,8 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
         __syncthreads();
         /* (a thread-local copy of the point was measured: spills, 3 % slower; the point as a kernel constant, for
          * launches with one point: constant-bank loads in divergent code, 4-7 % slower than these shared loads) */
-        const RaPointDev& pt = sPt;
-        RaJob job; job.pt = &pt; job.rep = a.jobRep[jobId];
+        const PT& pt = static_cast<const PT&>(sPt);
+        RaJobT<PT> job; job.pt = &pt; job.rep = a.jobRep[jobId];
         job.dump = DUMP ? a.dump + (size_t)jobId * a.dumpStride : nullptr;
         ra_job_init<DUMP>(job, s, tid, nt);
         RaAcc acc; acc.contFailed = acc.collP = acc.txop = acc.collScans = acc.totScans = 0;
@@ -386,9 +394,17 @@ struct RaDev {
     int hErr = 0;
 };
 
-static const void* ra_step_entry(bool dump, bool big) {
-    if (dump) return big ? (const void*)ra_step_kernel<true, RA_NT_BIG, RA_MINB_BIG> : (const void*)ra_step_kernel<true, RA_NT, RA_MINB>;
-    return big ? (const void*)ra_step_kernel<false, RA_NT_BIG, RA_MINB_BIG> : (const void*)ra_step_kernel<false, RA_NT, RA_MINB>;
+/* shape: 0 = 128 x 8, 1 = 256 x 5, 2 = 512 x 2 (threads x resident blocks per SM) */
+static const int kShapeNT[3] = {RA_NT, RA_NT_BIG, RA_NT_HUGE};
+static const int kShapeMinB[3] = {RA_MINB, RA_MINB_BIG, RA_MINB_HUGE};
+template <bool DUMP, bool FIXED>
+static const void* ra_step_entry2(int shape) {
+    if (shape == 2) return (const void*)ra_step_kernel<DUMP, RA_NT_HUGE, RA_MINB_HUGE, FIXED>;
+    return shape == 1 ? (const void*)ra_step_kernel<DUMP, RA_NT_BIG, RA_MINB_BIG, FIXED> : (const void*)ra_step_kernel<DUMP, RA_NT, RA_MINB, FIXED>;
+}
+static const void* ra_step_entry(bool dump, int shape, bool fixed) {
+    if (dump) return fixed ? ra_step_entry2<true, true>(shape) : ra_step_entry2<true, false>(shape);
+    return fixed ? ra_step_entry2<false, true>(shape) : ra_step_entry2<false, false>(shape);
 }
 
 struct ra_sim {
@@ -492,14 +508,26 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     if (d.smem > (size_t)prop.sharedMemPerBlockOptin) {
         sim->err = "per-replication tables (ring x preambles) exceed the shared memory of one block"; return RA_E_INVAL;
     }
-    /* W: the small block shape if RA_MINB blocks' tables (+1 KB reserved per block) fit in one SM, else the big one
-     * (RACH_BLOCK=big|small overrides, for tuning) */
-    bool big = (d.smem + 1024) * RA_MINB > (size_t)prop.sharedMemPerMultiprocessor;
-    if (const char* bs = getenv("RACH_BLOCK")) big = bs[0] == 'b';
-    d.nt = isN ? RA_NT_N : (big ? RA_NT_BIG : RA_NT);
-    const int minb = isN ? RA_MINB_N : (big ? RA_MINB_BIG : RA_MINB);
+    /* W block shape.  Enough replications to fill the device: 128 x 8 if eight blocks' tables (+1 KB reserved per block)
+     * fit in one SM's shared memory, else 256 x 5.  Fewer replications than block slots (strong scaling over GPUs, small
+     * sweeps): a replication cannot be split over blocks, so the blocks grow with the free room -- at most 5 per SM:
+     * 256 threads, at most 2 per SM: 512 threads.  RACH_BLOCK=small|big|huge overrides, for tuning. */
+    int shape = (d.smem + 1024) * RA_MINB > (size_t)prop.sharedMemPerMultiprocessor ? 1 : 0;
+    {
+        const int perSMjobs = (nJobs + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+        if (perSMjobs <= RA_MINB_HUGE) shape = 2;
+        else if (perSMjobs <= RA_MINB_BIG) shape = 1;
+    }
+    if (const char* bs = getenv("RACH_BLOCK")) shape = bs[0] == 'h' ? 2 : (bs[0] == 'b' ? 1 : 0);
+    /* all points in the reference's default family (P 54, BI 20, subframe 5, RAR window 5): the instantiation with those
+     * values as immediates (RACH_FIXED=0 forces the general one, for cross-checks) */
+    bool fixed = !isN;
+    for (const RaPointDev& hp : sim->hostPoints) fixed = fixed && ra_point_is_default_family(hp);
+    if (const char* fx = getenv("RACH_FIXED")) fixed = fixed && fx[0] != '0';
+    d.nt = isN ? RA_NT_N : kShapeNT[shape];
+    const int minb = isN ? RA_MINB_N : kShapeMinB[shape];
     const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
-                           : ra_step_entry(dump, big);
+                           : ra_step_entry(dump, shape, fixed);
     d.kern = kern;
     RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
     /* the driver's default carveout heuristic was the best of {default, 50, 60, 75, 100 %} (within 0.6 %);

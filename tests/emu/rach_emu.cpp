@@ -20,6 +20,47 @@ extern "C" {
 #include "ref_api.h"
 }
 
+extern "C" { int emu_use_fixed = 1; }
+
+template <bool DUMP, class PT>
+static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config* cfg, ref_result* res, int* perUE, int NT) {
+    RaJobT<PT> job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
+    std::vector<RaAcc> acc(NT); memset(acc.data(), 0, sizeof(RaAcc) * NT);
+
+    for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
+    int simTime = pt.maxTime;
+    for (int T = 0;; ++T) {
+        for (int t = 0; t < NT; ++t) ra_phase0(job, s, T, t, NT);
+        unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
+        if (s.nC3) ra_phase2_serial(pt, w, s);
+        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
+        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
+        unsigned n4 = (unsigned)pt.P + s.nLanders;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
+        if (s.nSingles) ra_phase5_serial(pt, w, s);
+        unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
+        if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
+        if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
+        if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
+        if (ra_ms_done(pt, s, T, &simTime)) break;
+    }
+    const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
+    if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
+    for (int t = 0; t < NT; ++t) {
+        s.contFailed += acc[t].contFailed; s.collP += acc[t].collP; s.txop += acc[t].txop;
+        s.collScans += acc[t].collScans; s.totScans += acc[t].totScans;
+    }
+    memset(res, 0, sizeof *res);
+    res->simTimeMs = simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
+    res->delaySum = (long long)s.delaySum; res->failCountSum = (long long)s.failSum;
+    res->continueFailed = (long long)s.contFailed; res->collisionPreambles = (long long)s.collP;
+    res->totalPreambleTxop = (long long)s.txop; res->collisionScans = (long long)s.collScans;
+    res->totalScans = (long long)s.totScans; res->captured = 1; res->lastMs = last;
+    return 0;
+}
+
 template <bool DUMP>
 static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT) {
     ra_params p; ra_params_default(&p, RA_VARIANT_W);
@@ -57,41 +98,11 @@ static int emu_run_t(const ref_config* cfg, ref_result* res, int* perUE, int NT)
     std::vector<uint4> smem((pt.smemBytes + 15) / 16 + 1);         /* the block's dynamic shared memory (ra_layout) */
     ra_emu_smem_base = reinterpret_cast<unsigned char*>(smem.data());
 
-    RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
-    std::vector<RaAcc> acc(NT); memset(acc.data(), 0, sizeof(RaAcc) * NT);
-
-    for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
-    int simTime = pt.maxTime;
-    for (int T = 0;; ++T) {
-        for (int t = 0; t < NT; ++t) ra_phase0(job, s, T, t, NT);
-        unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
-        if (s.nC3) ra_phase2_serial(pt, w, s);
-        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
-        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
-        unsigned n4 = (unsigned)pt.P + s.nLanders;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
-        if (s.nSingles) ra_phase5_serial(pt, w, s);
-        unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
-        if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
-        if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
-        if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
-        if (ra_ms_done(pt, s, T, &simTime)) break;
-    }
-    const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
-    if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
-    for (int t = 0; t < NT; ++t) {
-        s.contFailed += acc[t].contFailed; s.collP += acc[t].collP; s.txop += acc[t].txop;
-        s.collScans += acc[t].collScans; s.totScans += acc[t].totScans;
-    }
-    memset(res, 0, sizeof *res);
-    res->simTimeMs = simTime; res->nSuccess = (int)s.nSuccess; res->preambleTxSum = (long long)s.txSum;
-    res->delaySum = (long long)s.delaySum; res->failCountSum = (long long)s.failSum;
-    res->continueFailed = (long long)s.contFailed; res->collisionPreambles = (long long)s.collP;
-    res->totalPreambleTxop = (long long)s.txop; res->collisionScans = (long long)s.collScans;
-    res->totalScans = (long long)s.totScans; res->captured = 1; res->lastMs = last;
-    return 0;
+    /* the kernel's two views of a point: runtime values, or the compile-time family of the reference defaults */
+    int rc;
+    if (emu_use_fixed && ra_point_is_default_family(pt)) rc = emu_body<DUMP>(static_cast<const RaPointDef&>(pt), w, s, cfg, res, perUE, NT);
+    else rc = emu_body<DUMP>(pt, w, s, cfg, res, perUE, NT);
+    return rc;
 }
 
 extern "C" { int emu_threads = 64; }

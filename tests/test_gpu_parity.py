@@ -96,28 +96,53 @@ def test_fuzz_against_oracle(pkg, oracle):
         np.testing.assert_array_equal(ue, ue_ref, err_msg=str(kw))
 
 
-def test_both_block_shapes(pkg, oracle, monkeypatch):
-    """The W step kernel has two instantiations (128 x 8 and 256 x 5 threads x blocks/SM, picked by table size);
-    RACH_BLOCK forces one.  Both must reproduce the oracle, with and without the per-UE dump."""
+def test_every_kernel_instantiation(pkg, oracle, monkeypatch):
+    """The W step kernel has three block shapes (128 x 8, 256 x 5, 512 x 2 threads x blocks/SM, picked by table size and
+    by how many replications there are per SM; RACH_BLOCK forces one) and two views of the parameter point (the
+    reference's default family P 54 / BI 20 / subframe 5 / RAR window 5 as compile-time immediates, or runtime values;
+    RACH_FIXED=0 forces the runtime view).  Every combination must reproduce the oracle, with and without the per-UE
+    dump."""
     cases = [dict(nUE=6000, seed=11, rep=3), dict(nUE=2500, nPreamble=64, backoffIndicator=40, nGrantUL=4, seed=12),
-             dict(nUE=3000, distribution=1, nPreamble=3, maxRarWindow=9, accessTime=7, seed=13, geometry=1)]
+             dict(nUE=3000, distribution=1, nPreamble=3, maxRarWindow=9, accessTime=7, seed=13, geometry=1),
+             dict(nUE=9000, maxMsg2TxCount=49, nGrantUL=3, seed=15), dict(nUE=4000, distribution=1, seed=16, geometry=0)]
     for kw in cases:
         res, ue_ref, _ = oracle.run_port(oracle.make_config(**kw))
-        for shape in ("big", "small"):
-            monkeypatch.setenv("RACH_BLOCK", shape)
-            st, ue, _ = _run_gpu(pkg, kw)
-            st2, _, _ = _run_gpu(pkg, kw, dump=False)
-            for k in KEYS:
-                assert getattr(st, k) == getattr(res, k) == getattr(st2, k), (k, shape, kw)
-            np.testing.assert_array_equal(ue, ue_ref, err_msg="%s %s" % (shape, kw))
+        for shape in ("huge", "big", "small"):
+            for fixed in ("1", "0"):
+                monkeypatch.setenv("RACH_BLOCK", shape)
+                monkeypatch.setenv("RACH_FIXED", fixed)
+                st, ue, _ = _run_gpu(pkg, kw)
+                st2, _, _ = _run_gpu(pkg, kw, dump=False)
+                for k in KEYS:
+                    assert getattr(st, k) == getattr(res, k) == getattr(st2, k), (k, shape, fixed, kw)
+                np.testing.assert_array_equal(ue, ue_ref, err_msg="%s %s %s" % (shape, fixed, kw))
     monkeypatch.delenv("RACH_BLOCK")
-    # a point whose tables do not fit 8 times in one SM takes the big shape by itself
+    monkeypatch.delenv("RACH_FIXED")
+    # a point whose tables do not fit 8 times in one SM takes a larger shape by itself
     kw = dict(nUE=4000, nPreamble=64, backoffIndicator=100, seed=14)
     res, ue_ref, _ = oracle.run_port(oracle.make_config(**kw))
     st, ue, _ = _run_gpu(pkg, kw)
     for k in KEYS:
         assert getattr(st, k) == getattr(res, k), (k, kw)
     np.testing.assert_array_equal(ue, ue_ref)
+
+
+def test_shape_follows_the_job_count(pkg, oracle):
+    """Default-family points, enough replications for every automatic shape choice: 1 per SM (512-thread blocks),
+    4 per SM (256), 8+ per SM (128).  Same tape ids -> the same per-replication counters whatever the shape."""
+    p = pkg.default_params(nUE=1500, seed=21)
+    ref = None
+    for reps in (1300, 600, 100):
+        with pkg.RachSim([p], reps=reps, devices=[0], rep_offset=50) as sim:
+            sim.run()
+            st = sim.stats_all()[0]
+        if ref is None:
+            ref = st
+            for rep in (0, 777, 1299):
+                res, _, _ = oracle.run_port(oracle.make_config(nUE=1500, seed=21, rep=50 + rep), per_ue=False)
+                for k in KEYS:
+                    assert int(st[rep][k]) == getattr(res, k), (rep, k)
+        assert (st == ref[:reps]).all(), reps
 
 
 def test_against_reference_sources_in_tape_mode(pkg, oracle):
