@@ -30,6 +30,7 @@
 
 #include <math.h>
 #include "rach_core.cuh"
+#include "rach_warp.cuh"
 
 #ifdef __CUDA_ARCH__
 #define RA_FMUL(a, b) __fmul_rn((a), (b))
@@ -79,6 +80,7 @@ struct RaSharedN {
     int*      sIdx;      /* [6*P] ... UE index (-1 = paired away, N:280-281)                  */
     double*   sLg;       /* [6*P] ... 10*log(channelGain)                                     */
     double*   sGain;     /* [6*P] ... channelGain                                             */
+    unsigned* ord;       /* [6*P] ... the singles in ascending gain order (positions into sPos/sIdx/sGain) */
     int activeCheck, acOld, nArr, overflow;
     unsigned nSuccess, nZombie, nDropped, pad;
     ra_u64 txSum, delaySum;
@@ -242,6 +244,92 @@ RA_HD void rn_phaseB_sector(const RaJob& job, const RaWorkN& w, RaSharedN& s, in
     (void)pair;                                             /* count - pair > 0 whenever an unpaired single is left */
     for (int i = 0; i < count && grants < G; ++i)           /* N:299-307 */
         if (sIdx[i] != -1) { grants++; s.grant[sec * P + sPos[i]] = 1; }
+}
+
+/* ---- occasion phase B, warp form: ONE WARP decides one sector (same decisions as rn_phaseB_sector above, which stays
+ * as the one-thread statement of N:243-309 for cross-checks).  Written in the vector form of rach_warp.cuh.
+ *   gather   singles in preamble order: ballot + prefix count per 32 preambles (N:244-249)
+ *   sort     sortUE (N:90-103) is a stable ascending sort by channelGain: every single counts the singles that sort
+ *            before it (gain, then position) and takes that rank -- O(count) per lane instead of O(count^2) on one
+ *   pairing  N:268-298 walks the sorted singles i = 0.. and pairs i with the FIRST j >= 1 still unpaired whose
+ *            10*log(gain_j) - 10*log(gain_i) > 15.: one ballot per 32 candidates; the base-station draws (N:284,286) are
+ *            keyed (sector, ms, k) and computed redundantly by every lane
+ *   rest     N:299-307: unpaired singles in gain order while the sector has grants left: ballot + prefix count */
+RW_FN void rn_phaseB_warp(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, int sec) {
+    const RaPointDev& pt = *job.pt;
+    const int P = pt.P, G = pt.G;
+    unsigned* sPos = s.sPos + sec * P; int* sIdx = s.sIdx + sec * P; unsigned* ord = s.ord + sec * P;
+    double* sLg = s.sLg + sec * P; double* sGain = s.sGain + sec * P;
+    const uint4* bT = w.bucket + (size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap;
+    const bool nonSector = pt.geometry == 0;
+    int f[RW_LANES];
+    int count = 0;
+    for (int base = 0; base < P; base += 32) {
+        RW_EACH(l) { const int p = base + lane; f[l] = p < P && s.cnt[sec * P + p] == 1; }
+        const unsigned mask = RW_BALLOT(f);
+        RW_EACH(l) if (f[l]) {
+            const int p = base + lane, k = count + RW_POPC(mask & ((1u << lane) - 1u));
+            const int idx = (int)bT[s.who[sec * P + p]].x;
+            sPos[k] = (unsigned)p; sIdx[k] = idx; sGain[k] = w.gain[idx];
+        }
+        count += RW_POPC(mask);
+    }
+    RW_SYNC();
+    if (count == 0) return;
+    if (count <= G) {                                       /* N:252-260 / N:377-384: every single is answered */
+        RW_EACH(l) for (int i = lane; i < count; i += 32) s.grant[sec * P + sPos[i]] = 1;
+        return;
+    }
+    RW_EACH(l) for (int i = lane; i < count; i += 32) {
+        const double g = sGain[i];
+        int rank = 0;
+        for (int j = 0; j < count; ++j) { const double h = sGain[j]; rank += (h < g || (h == g && j < i)) ? 1 : 0; }
+        ord[rank] = (unsigned)i;
+        sLg[i] = RA_DMUL(10.0, log(g));
+    }
+    RW_SYNC();
+    int grants = 0;
+    unsigned bsK = 0;
+    for (int ri = 0; ri < count - 1 && grants < G; ++ri) {  /* N:268-298; nothing changes any UE once the grants are gone */
+        const unsigned ei = ord[ri];
+        if (sIdx[ei] == -1) continue;
+        const double lgi = sLg[ei];
+        int rj = -1;
+        for (int base = 0; base < count && rj < 0; base += 32) {
+            RW_EACH(l) {
+                const int r = base + lane;
+                f[l] = 0;
+                if (r >= 1 && r < count) { const unsigned e = ord[r]; f[l] = sIdx[e] != -1 && RA_DSUB(sLg[e], lgi) > 15.; }
+            }
+            const unsigned mask = RW_BALLOT(f);
+            if (mask) rj = base + RW_FFS(mask) - 1;
+        }
+        if (rj < 0) continue;
+        const unsigned ej = ord[rj], pi_ = sPos[ei], pj_ = sPos[ej];
+        RW_SYNC();                                          /* every lane has read the marks of this round */
+        grants++;
+        const int r0 = rach_tape_rand31(pt.seed, job.rep, (unsigned)sec, (unsigned)T, bsK++, RACH_TAPE_TAG_BS);
+        const double pr = (double)r0 / (double)2147483647;                                     /* N:284 */
+        unsigned g0 = pi_, g1 = pj_;                        /* N:290-291: both */
+        if (pr < 0.3) {
+            if (nonSector) g1 = pi_;                                                          /* N:413-415 */
+            else {
+                const int r1 = rach_tape_rand31(pt.seed, job.rep, (unsigned)sec, (unsigned)T, bsK++, RACH_TAPE_TAG_BS);
+                g0 = g1 = (r1 % 2) ? pj_ : pi_;                                               /* N:286-287 */
+            }
+        }
+        RW_EACH(l) if (lane == 0) {
+            sIdx[ei] = -1; sIdx[ej] = -1;
+            s.grant[sec * P + g0] = 1; s.grant[sec * P + g1] = 1;
+        }
+        RW_SYNC();
+    }
+    for (int base = 0; base < count && grants < G; base += 32) {                              /* N:299-307 */
+        RW_EACH(l) { const int r = base + lane; f[l] = r < count && sIdx[ord[r]] != -1; }
+        const unsigned mask = RW_BALLOT(f);
+        RW_EACH(l) if (f[l] && grants + RW_POPC(mask & ((1u << lane) - 1u)) < G) s.grant[sec * P + sPos[ord[base + lane]]] = 1;
+        grants += RW_POPC(mask);
+    }
 }
 
 /* ---- occasion phase C: msg2Results(UE, T+1) for every transmitter, N:449-498 ---- */

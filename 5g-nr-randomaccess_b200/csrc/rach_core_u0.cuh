@@ -23,6 +23,7 @@
 #define RACH_CORE_U0_CUH
 
 #include "rach_core.cuh"
+#include "rach_warp.cuh"
 
 #ifdef __CUDACC__
 #define RU_ALIGN __align__(16)
@@ -187,34 +188,7 @@ RA_HD void ru_serial_ms(const RaJob& job, RuUE* live, RuUE* win, int winCap, RuU
     }
 }
 
-/* ---- vector form ------------------------------------------------------------------------------------------- */
-#ifdef __CUDA_ARCH__
-#define RW_LANES 1
-#define RW_EACH(l) for (int l = 0, lane = (int)(threadIdx.x & 31u); l < 1 && ((void)lane, true); ++l)
-#define RW_BALLOT(arr) __ballot_sync(0xFFFFFFFFu, (arr)[0])
-#define RW_SHFL(arr, src) __shfl_sync(0xFFFFFFFFu, (arr)[0], (src))
-#define RW_SYNC() __syncwarp()
-#define RW_POPC(x) __popc(x)
-#define RW_FFS(x) __ffs((int)(x))
-#define RW_FN __device__ __forceinline__
-RW_FN long long rw_sum(const long long* a) {
-    long long v = a[0];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    return v;
-}
-#else
-#define RW_LANES 32
-#define RW_EACH(l) for (int l = 0, lane = 0; l < 32 && ((void)lane, true); ++l, lane = l)
-static inline unsigned rw_ballot(const int* a) { unsigned m = 0; for (int i = 0; i < 32; ++i) if (a[i]) m |= 1u << i; return m; }
-#define RW_BALLOT(arr) rw_ballot(arr)
-#define RW_SHFL(arr, src) ((arr)[(src)])
-#define RW_SYNC() ((void)0)
-#define RW_POPC(x) __builtin_popcount(x)
-#define RW_FFS(x) __builtin_ffs((int)(x))
-#define RW_FN static inline
-static inline long long rw_sum(const long long* a) { long long v = 0; for (int i = 0; i < 32; ++i) v += a[i]; return v; }
-#endif
-
+/* ---- vector form (rach_warp.cuh) ---------------------------------------------------------------------------- */
 /* per-lane partial sums, folded at the end of the replication */
 struct RuLaneSums { long long txSum[RW_LANES], delaySum[RW_LANES], coll[RW_LANES], txop[RW_LANES], dropped[RW_LANES]; };
 

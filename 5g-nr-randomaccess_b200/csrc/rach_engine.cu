@@ -230,11 +230,12 @@ __device__ __forceinline__ void rn_carve(RaSharedN& s, unsigned char* base, int 
     s.grant = reinterpret_cast<unsigned*>(base); base += sizeof(unsigned) * c;
     s.sPos = reinterpret_cast<unsigned*>(base);  base += sizeof(unsigned) * c;
     s.sIdx = reinterpret_cast<int*>(base);       base += sizeof(int) * c;
+    s.ord = reinterpret_cast<unsigned*>(base);   base += sizeof(unsigned) * c;
     s.bcount = reinterpret_cast<unsigned*>(base); base += sizeof(unsigned) * (size_t)R;
     s.m3count = reinterpret_cast<unsigned*>(base);
 }
 static size_t rn_smem_bytes(int R, int P) {
-    return (size_t)RA_NSECT * P * (2 * sizeof(double) + 5 * sizeof(unsigned)) + sizeof(unsigned) * ((size_t)R + RA_M3RING);
+    return (size_t)RA_NSECT * P * (2 * sizeof(double) + 6 * sizeof(unsigned)) + sizeof(unsigned) * ((size_t)R + RA_M3RING);
 }
 
 template <bool DUMP>
@@ -269,8 +270,7 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
                 const unsigned nTx = s.bcount[(unsigned)T & Rm];
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
                 __syncthreads();
-                if ((tid & 31) == 0)
-                    for (int sec = tid >> 5; sec < (pt.geometry ? RA_NSECT : 1); sec += nt >> 5) rn_phaseB_sector(job, w, s, T, sec);
+                for (int sec = tid >> 5; sec < (pt.geometry ? RA_NSECT : 1); sec += nt >> 5) rn_phaseB_warp(job, w, s, T, sec);   /* one warp per sector */
                 __syncthreads();
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseC_item<DUMP>(job, w, s, T, j);
                 __syncthreads();

@@ -122,6 +122,8 @@ extern "C" int emu_run(const ref_config* cfg, ref_result* res, int* perUE, float
  * ------------------------------------------------------------------------------------------ */
 #include "rach_core_n.cuh"
 
+extern "C" { int emu_n_serialB = 0; }
+
 template <bool DUMP>
 static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, double* gains, int NT) {
     ra_params p; ra_params_default(&p, RA_VARIANT_N);
@@ -147,12 +149,12 @@ static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, doubl
     std::vector<double> gain(w.cap);
     w.bucket = bucket.data(); w.msg3 = msg3.data(); w.zombie = zombie.data(); w.gain = gain.data();
     const size_t c = (size_t)RA_NSECT * pt.P;
-    std::vector<unsigned> cnt(c), who(c), grant(c), sPos(c), bcount(pt.R), m3count(RA_M3RING);
+    std::vector<unsigned> cnt(c), who(c), grant(c), sPos(c), ord(c), bcount(pt.R), m3count(RA_M3RING);
     std::vector<int> sIdx(c);
     std::vector<double> sLg(c), sGain(c);
     RaSharedN s; memset(&s, 0, sizeof s);
     s.cnt = cnt.data(); s.who = who.data(); s.grant = grant.data(); s.sPos = sPos.data(); s.sIdx = sIdx.data();
-    s.sLg = sLg.data(); s.sGain = sGain.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
+    s.sLg = sLg.data(); s.sGain = sGain.data(); s.ord = ord.data(); s.bcount = bcount.data(); s.m3count = m3count.data();
     RaJob job; job.pt = &pt; job.rep = (unsigned)cfg->rep; job.dump = DUMP ? perUE : NULL;
 
     for (int t = 0; t < NT; ++t) rn_job_init<DUMP>(job, s, t, NT);
@@ -164,7 +166,9 @@ static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, doubl
             for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, i);
             const unsigned nTx = s.bcount[(unsigned)T & Rm];
             for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseA2_item(pt, w, s, T, j);
-            for (int sec = 0; sec < (pt.geometry ? RA_NSECT : 1); ++sec) rn_phaseB_sector(job, w, s, T, sec);
+            for (int sec = 0; sec < (pt.geometry ? RA_NSECT : 1); ++sec) {       /* warp form (the kernel's) or the one-thread statement */
+                if (emu_n_serialB) rn_phaseB_sector(job, w, s, T, sec); else rn_phaseB_warp(job, w, s, T, sec);
+            }
             for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseC_item<DUMP>(job, w, s, T, j);
             s.bcount[(unsigned)T & Rm] = 0;
         }

@@ -84,15 +84,24 @@ def test_noma_variant_emulated(oracle, emu):
                           maxMsg2TxCount=rnd.choice([1, 3, 10]), accessTime=rnd.choice([5, 5, 6, 10]),
                           maxRarWindow=rnd.choice([3, 5]), cellRadius=rnd.choice([100.0, 500.0]),
                           seed=rnd.getrandbits(60), rep=rnd.randrange(1000), geometry=rnd.choice([0, 1, 1])))
+    # more singles than 32 lanes per sector (non-sector function with 200 preambles), many grants, tiny radius range
+    cases += [dict(nUE=30000, nPreamble=200, nGrantUL=7, geometry=0, seed=5), dict(nUE=30000, nPreamble=256, nGrantUL=3, seed=6),
+              dict(nUE=12000, nPreamble=100, nGrantUL=40, geometry=0, seed=7), dict(nUE=50000, seed=8, rep=3)]
+    import ctypes
+    serial_b = ctypes.c_int.in_dll(ctypes.CDLL(so), "emu_n_serialB")
     zomb = 0
     for kw in cases:
         cfg = oracle.make_config_n(**kw)
         p, ue, g = oracle.run_port_n(cfg)
-        e, ue2, g2 = oracle._run_n(f, cfg)
-        for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum"):
-            assert getattr(p, k) == getattr(e, k), (k, kw)
-        np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
-        np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
+        # the base-station decision of a sector in its two forms: one warp (the kernel's), one thread
+        for mode in (0, 1):
+            serial_b.value = mode
+            e, ue2, g2 = oracle._run_n(f, cfg)
+            for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum"):
+                assert getattr(p, k) == getattr(e, k), (k, mode, kw)
+            np.testing.assert_array_equal(ue, ue2, err_msg="%s mode %d" % (kw, mode))
+            np.testing.assert_array_equal(g.view(np.uint64), g2.view(np.uint64))
+        serial_b.value = 0
         zomb += int(((ue[:, 1] == 1) & (ue[:, 14] > 0) & (ue[:, 15] == 0) & (ue[:, 2] < p.simTimeMs - 100)).sum())
     assert zomb > 0      # restarts that can never transmit again (NOMA.c:538 + :692) were exercised
 
