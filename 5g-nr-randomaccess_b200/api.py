@@ -32,7 +32,7 @@ class RaStats(C.Structure):
                 ("continueFailed", C.c_longlong), ("finalSuccess", C.c_longlong),
                 ("collisionPreambles", C.c_longlong), ("totalPreambleTxop", C.c_longlong),
                 ("collisionScans", C.c_longlong), ("totalScans", C.c_longlong),
-                ("updates", C.c_longlong)]
+                ("updates", C.c_longlong), ("recordMoves", C.c_longlong)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -42,7 +42,7 @@ STATS_DTYPE = np.dtype([("simTimeMs", "<i4"), ("nSuccess", "<i4"), ("preambleTxS
                         ("delaySum", "<i8"), ("failCountSum", "<i8"), ("continueFailed", "<i8"),
                         ("finalSuccess", "<i8"), ("collisionPreambles", "<i8"),
                         ("totalPreambleTxop", "<i8"), ("collisionScans", "<i8"),
-                        ("totalScans", "<i8"), ("updates", "<i8")])
+                        ("totalScans", "<i8"), ("updates", "<i8"), ("recordMoves", "<i8")])
 assert STATS_DTYPE.itemsize == C.sizeof(RaStats)
 
 

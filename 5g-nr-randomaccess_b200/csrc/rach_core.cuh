@@ -191,6 +191,7 @@ struct RaShared {
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant, nNl, pad1;
     ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
+    ra_u64 recMoves;          /* records read from the calendars (move buckets, Msg3 ring, same-ms work list)     */
 };
 
 /* per-thread counters, folded into RaShared at the end of the replication */
@@ -388,6 +389,7 @@ RA_HD void ra_job_init(const RaJobT<PT>& job, RaShared& s, int tid, int nt) {
         s.nextAc = pt.arrCum[0]; s.nextArrMs = 0; s.occ = 0;
         s.nSuccess = 0; s.noGrant = 0;
         s.txSum = s.delaySum = s.failSum = s.contFailed = s.collP = s.txop = s.collScans = s.totScans = 0;
+        s.recMoves = 0;
     }
 }
 
@@ -423,6 +425,7 @@ RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt)
         s.nArr = s.activeCheck - s.acOld;
         s.nMov = S_bcount[(unsigned)T & Rm];
         s.nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
+        s.recMoves += (ra_u64)s.nMov + s.nM3;
     }
 }
 
@@ -447,10 +450,9 @@ RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s
     const PT& pt = *job.pt;
     if (rec.x == RA_DEAD) return;
     const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
-    unsigned mrc = ra_rec_mrc(rec), ptc = ra_rec_ptc(rec);
     /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
     const bool uncertain = !stale && idx < S_l1[p0];
-    const bool limit = (int)mrc >= pt.M;
+    const bool limit = (int)ra_rec_mrc(rec) >= pt.M;
     /* both branches draw the backoff: retry W:540 (1st draw), limit W:514 (2nd draw) */
     const int tmp = (int)pt.modBI((limit ? d.v[1] : d.v[0]) >> 1);
     /* Both branches written as selects: one mover in ten takes the limit branch, so almost every warp would
@@ -458,18 +460,20 @@ RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s
      *   retry branch, W:532-558: subTime = time + tmp (W:542); maxRarCounter++, preambleTxCounter++
      *   limit branch, W:498-531: new preamble, counters reset, timer = 0, failCount++, subTime = CURRENT
      *     txTime + tmp (W:516): an old txTime if stale, T+1 if a lower index postponed me (certain above the
-     *     leader), T under the not-postponed hypothesis if uncertain (settled in phase 3) */
+     *     leader), T under the not-postponed hypothesis if uncertain (settled in phase 3)
+     * The counters are updated inside the packed words (no unpack / repack): retry adds 1 to maxRarCounter (bits 8..15;
+     * it is below M <= 255 here, so no carry) and to preambleTxCounter (bits 16..30; a carry into bit 31 is the overflow
+     * check), limit writes preamble | 0 << 8 | 1 << 16 and adds 1 to failCount (bits 16..31 of z; carry = overflow). */
     const unsigned pl = pt.modP(d.v[0] >> 1);
     const unsigned pnew = limit ? pl : p0;
-    const unsigned fail = ra_rec_fail(rec) + (limit ? 1u : 0u);
-    const unsigned z = limit ? ra_z((unsigned)T, fail) : rec.z;
-    mrc = limit ? 0u : mrc + 1u;
-    ptc = limit ? 1u : ptc + 1u;
+    const unsigned wRetry = (rec.w & 0x7FFFFFFFu) + 0x00010100u;
+    const unsigned nw = limit ? (pl | 0x00010000u) : wRetry;
+    const unsigned z = limit ? (((rec.z & 0xFFFF0000u) + 0x00010000u) | (unsigned)T) : rec.z;
     acc.contFailed += limit ? 1u : 0u;
     const int base = limit ? (stale ? (int)rec.y : (uncertain ? T : T + 1)) : T;
-    if (fail > 0xFFFFu || ptc > 0x7FFFu || mrc > 0xFFu) s.overflow = 2;
+    if (limit ? rec.z >= 0xFFFF0000u : (wRetry >> 31) != 0u) s.overflow = 2;
     const int X = ra_align_pt(pt, base + tmp);
-    const uint4 nr = make_uint4(idx, (unsigned)X, z, ra_w3(pnew, mrc, ptc, 0));
+    const uint4 nr = make_uint4(idx, (unsigned)X, z, nw);
     if (uncertain) {
         unsigned u = RA_AADD(&s.nUnc, 1u);
         ra_unc_set(pt, w, u, make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0));

@@ -30,15 +30,17 @@
 #include "rach_host.h"
 
 /* Block shapes of the W step kernel (threads, resident blocks per SM the register budget is sized for).
- * Measured on B200, 4096 replications x 100k UEs: 128 x 8 (64 registers, no spills) 1215 ms, 256 x 5 (48 registers)
- * 1259 ms, 192 x 6 1241 ms, 96 x 10 1286 ms, 64 x 11 1337 ms, 512 x 2 1515 ms -- the block-wide barriers between
- * the phases cost less with 4 warps than with 8.  The small shape needs 8 blocks' tables in one SM's shared
- * memory; points with a large ring x preamble product fall back to 256 x 5 (fewer, larger blocks). */
+ * Measured on B200, 4096 replications x 100k UEs, round 1 (runtime parameters): 128 x 8 (64 registers, no spills) 1215 ms,
+ * 256 x 5 (48 registers) 1259 ms, 192 x 6 1241 ms, 96 x 10 1286 ms, 64 x 11 1337 ms, 512 x 2 1515 ms -- the block-wide
+ * barriers between the phases cost less with 4 warps than with 8.  Round 2, default-family instantiation (compile-time
+ * P / BI / subframe / window): 128 x 8 1061 ms, 128 x 9 (56 registers) 1030 ms, 128 x 10 1050 ms, 96 x 10 1102 ms.
+ * The small shape needs its blocks' tables in one SM's shared memory; points with a large ring x preamble product fall
+ * back to 256 x 5 (fewer, larger blocks). */
 #ifndef RA_NT
 #define RA_NT 128          /* small shape */
 #endif
 #ifndef RA_MINB
-#define RA_MINB 8
+#define RA_MINB 9
 #endif
 #define RA_NT_BIG 256
 #define RA_MINB_BIG 5
@@ -47,8 +49,9 @@
 #define RA_NT_HUGE 512
 #define RA_MINB_HUGE 2
 #ifndef RA_NT_N
-#define RA_NT_N 192        /* variant N: phase B runs one warp leader per sector, 6 warps = 6 sectors.  Measured */
-#define RA_MINB_N 5        /* (50k UEs x 2048 replications): 192 x 5 169 ms, 128 x 8 174 ms, 256 x 4 203 ms    */
+#define RA_NT_N 128        /* variant N, one warp per sector in the base-station phase.  Measured (50k UEs x 2048 replications,  */
+#define RA_MINB_N 8        /* round 2): 128 x 8 57.0 ms, 96 x 10 57.5 ms, 192 x 5 63.6 ms, 256 x 4 76.2 ms (round 1, one lane per
+                              sector: 192 x 5 169 ms) */
 #endif
 #define RA_NPHASE 10
 #ifndef RA_ILP
@@ -120,22 +123,25 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                 const uint4 dead = make_uint4(RA_DEAD, 0, 0, 0);
                 unsigned i = tid;
 #if RA_ILP >= 2
+                /* the thread walks records tid, tid + NT, ...: one pointer stepped by a compile-time stride (loads at
+                 * immediate offsets), `left` = records from the thread's current one to the end of the bucket */
+                const uint4* pr = bT + tid;
+                int left = (int)nMov - tid;
                 uint4 c[RA_ILP];
 #pragma unroll
-                for (int k = 0; k < RA_ILP; ++k) c[k] = i + k * nt < nMov ? bT[i + k * nt] : dead;
-                while (i < nMov) {
-                    const unsigned ni = i + RA_ILP * nt;
+                for (int k = 0; k < RA_ILP; ++k) c[k] = left > k * NT ? pr[k * NT] : dead;
+                while (left > 0) {
                     uint4 n[RA_ILP];
                     rach_u32x4 d[RA_ILP];
 #pragma unroll
-                    for (int k = 0; k < RA_ILP; ++k) n[k] = ni + k * nt < nMov ? bT[ni + k * nt] : dead;
+                    for (int k = 0; k < RA_ILP; ++k) n[k] = left > (RA_ILP + k) * NT ? pr[(RA_ILP + k) * NT] : dead;
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) d[k] = ra_draws(job, c[k].x, T);
 #pragma unroll
-                    for (int k = 0; k < RA_ILP; ++k) ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * nt, c[k], d[k]);
+                    for (int k = 0; k < RA_ILP; ++k) ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * NT, c[k], d[k]);
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) c[k] = n[k];
-                    i = ni;
+                    i += RA_ILP * NT; pr += RA_ILP * NT; left -= RA_ILP * NT;
                 }
 #else
                 uint4 c0 = i < nMov ? bT[i] : dead;
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
         if (acc.totScans) atomicAdd(&s.totScans, (ra_u64)acc.totScans);
         __syncthreads();
         if (tid == 0) {
-            ra_stats st;
+            ra_stats st; memset(&st, 0, sizeof st);
             st.simTimeMs = simTime; st.nSuccess = (int)s.nSuccess;
             st.preambleTxSum = (long long)s.txSum; st.delaySum = (long long)s.delaySum;
             st.failCountSum = (long long)s.failSum; st.continueFailed = (long long)s.contFailed;
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             st.collisionPreambles = (long long)s.collP; st.totalPreambleTxop = (long long)s.txop;
             st.collisionScans = (long long)s.collScans; st.totalScans = (long long)s.totScans;
             st.updates = (long long)pt.nUE * (long long)((simTime + pt.A - 1) / pt.A);
+            st.recordMoves = (long long)s.recMoves;
             a.stats[jobId] = st;
             if (s.overflow) atomicExch(a.errFlag, s.overflow);
         }
@@ -514,9 +521,17 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
      * 256 threads, at most 2 per SM: 512 threads.  RACH_BLOCK=small|big|huge overrides, for tuning. */
     int shape = (d.smem + 1024) * RA_MINB > (size_t)prop.sharedMemPerMultiprocessor ? 1 : 0;
     {
+        /* larger blocks only pay where a ms has hundreds of events to share out; a lightly loaded point (Uniform traffic:
+         * 9 arrivals per occasion at 100k UEs) is barrier latency, which grows with the block (measured, Uniform 100k x 256:
+         * 128 threads 129 ms, 256 137 ms, 512 143 ms) */
+        int peak = 0;
+        for (const std::vector<int>& ac : sim->arrCum)
+            for (size_t o = 0; o < ac.size(); ++o) peak = std::max(peak, ac[o] - (o ? ac[o - 1] : 0));
         const int perSMjobs = (nJobs + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-        if (perSMjobs <= RA_MINB_HUGE) shape = 2;
-        else if (perSMjobs <= RA_MINB_BIG) shape = 1;
+        if (peak >= 24) {
+            if (perSMjobs <= RA_MINB_HUGE) shape = 2;
+            else if (perSMjobs <= RA_MINB_BIG) shape = 1;
+        }
     }
     if (const char* bs = getenv("RACH_BLOCK")) shape = bs[0] == 'h' ? 2 : (bs[0] == 'b' ? 1 : 0);
     /* all points in the reference's default family (P 54, BI 20, subframe 5, RAR window 5): the instantiation with those

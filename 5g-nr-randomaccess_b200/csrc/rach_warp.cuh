@@ -1,7 +1,7 @@
 /*
  * rach_warp.cuh -- "vector form" helpers: code written once that runs as one warp on the device (one lane per
  * element, ballots and shuffles) and as a loop over 32 emulated lanes on the host (tests/emu), so that warp-level
- * formulations can be fuzzed against the oracle on the CPU before they ever run on a GPU.
+ * formulations can be fuzzed on the CPU against the CPU restatement of the reference (test infrastructure) before they ever run on a GPU.
  *
  *   RW_EACH(l) { ... lane ... x[l] ... }   per-lane statement block: on the device l == 0 and lane is the lane id,
  *                                          on the host l == lane runs over 0..31; per-lane values live in arrays

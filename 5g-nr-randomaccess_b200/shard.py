@@ -7,7 +7,7 @@ are summed.  Reference: the seed loop and the nUE sweep are independent iteratio
 import numpy as np
 
 COUNTER_KEYS = ("updates", "nSuccess", "preambleTxSum", "delaySum", "failCountSum", "continueFailed",
-                "collisionPreambles", "totalPreambleTxop")
+                "collisionPreambles", "totalPreambleTxop", "recordMoves")
 
 
 def shard_plan(reps, world, rank, scaling="weak"):

@@ -99,6 +99,10 @@ class ClockSampler:
 # CPU baseline: the REFERENCE's own code (oracle/_ref/libref_w.so, compiled from
 # /root/reference/RandomAccessWithNOMA.c by oracle/build_ref.sh) with its own libc rand().
 # ------------------------------------------------------------------------------------------------
+SAMPLE_MS = 1000        # the ONE prefix length of every CPU sample at the headline size (both arms, any --steps)
+FULL_NUE = 30000        # a complete replication is affordable on the CPU at this size (about a minute per core)
+
+
 def _ref_worker(args):
     nue, stop_ms, seed = args
     from oracle import oracle as O
@@ -111,11 +115,12 @@ def _ref_worker(args):
         r, _, _ = O.run_port(cfg, per_ue=False)
     dt = time.perf_counter() - t
     ms_done = stop_ms if stop_ms > 0 else r.simTimeMs
-    return kind, nue * ((ms_done + 4) // 5), dt
+    return kind, nue * ((ms_done + 4) // 5), dt, r.nSuccess
 
 
 def cpu_reference_sample(nue, stop_ms, procs):
-    """One process per core, distinct seeds, each the first `stop_ms` ms of a replication."""
+    """The reference's own code (libc rand()), one process per core, distinct seeds; each process runs the first
+    `stop_ms` ms of a replication, or a complete replication when stop_ms == 0."""
     import multiprocessing as mp
     from oracle import oracle as O
     O.build()
@@ -125,12 +130,16 @@ def cpu_reference_sample(nue, stop_ms, procs):
     wall = time.perf_counter() - t
     updates = sum(o[1] for o in out)
     kind = out[0][0]
+    if stop_ms > 0:
+        what = ("first %d ms (%d occasions) of a %d-UE Beta replication (a complete one takes ~14 min per core); the "
+                "prefix is the cheap part of the run (before the Beta peak), so this number FLATTERS the CPU"
+                % (stop_ms, (stop_ms + 4) // 5, nue))
+    else:
+        what = "one COMPLETE %d-UE Beta replication (10 000 ms, %d occasions)" % (nue, 2000)
     return {"value": updates / wall, "unit": "updates/s", "cores": procs, "kind": kind,
-            "sample": "first %d ms (%d occasions) of a %d-UE Beta replication, one process per core, "
-                      "%d replications, libc rand(); early ms are the cheap ones, so this flatters the CPU "
-                      "(full replication: SURVEY section 6, 2.3e5 updates/s on one core)"
-                      % (stop_ms, (stop_ms + 4) // 5, nue, procs),
-            "wall_s": wall, "single_thread_value": max(o[1] / o[2] for o in out)}
+            "sample": "%s; one process per core, %d replications, libc rand()" % (what, procs),
+            "wall_s": wall, "single_thread_value": max(o[1] / o[2] for o in out),
+            "mean_success": sum(o[3] for o in out) / len(out)}
 
 
 def run_reference_arm(args):
@@ -139,11 +148,9 @@ def run_reference_arm(args):
         return
     procs = os.cpu_count() or 1
     total = args.steps + args.warmup
-    # per-core seconds measured in the build container for stop_ms: 1500 -> 18 s, 1000 -> 8 s, 600 -> 3 s
-    stop_ms = 1500 if total <= 8 else (1000 if total <= 20 else 600)
     vals = []
     for i in range(total):
-        s = cpu_reference_sample(args.nue, stop_ms, procs)
+        s = cpu_reference_sample(args.nue, SAMPLE_MS, procs)
         if i >= args.warmup:
             vals.append(s)
     updates_per_s = sum(v["value"] for v in vals) / len(vals)
@@ -153,12 +160,38 @@ def run_reference_arm(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "config": {"workload": "100k UEs, Beta 10 s, W defaults (54 preambles, BI 20, 12 grants, RAR 5, retx 10)",
-                       "nUE": args.nue, "sample_ms": stop_ms, "replications_per_step": procs},
+                       "nUE": args.nue, "sample_ms": SAMPLE_MS, "replications_per_step": procs,
+                       "same_work_as_gpu_arm": False,
+                       "note": "a step here is the first %d ms of one replication per host core (bounded sample, the cheap "
+                               "prefix); the GPU arm's step is 4096 complete replications.  The like-for-like CPU/GPU "
+                               "pair is cpu_baseline.full_replication in the GPU arm's line" % SAMPLE_MS},
             "cpu_baseline": {"value": updates_per_s, "unit": "updates/s", "cores": procs,
                              "kind": vals[0]["kind"], "sample": vals[0]["sample"]},
             "e2e": {"value": updates_per_s, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def full_replication_pair(pkg, device, procs):
+    """The like-for-like CPU/GPU pair: COMPLETE replications at a size the CPU can finish (FULL_NUE UEs, Beta 10 s,
+    W defaults, overloaded regime: ~60 % success), the reference's code on every host core and the engine on the GPU."""
+    cpu = cpu_reference_sample(FULL_NUE, 0, procs)
+    reps = 2048
+    p = pkg.default_params(nUE=FULL_NUE)
+    with pkg.RachSim([p], reps=reps, devices=[device]) as sim:
+        sim.run()
+        sim.run()
+        st = sim.stats_all()
+        kms = sim.kernel_ms
+    gpu_val = float(st["updates"].sum()) / (kms / 1e3)
+    return {"nUE": FULL_NUE, "what": "complete replications on both sides (no prefix): the apples-to-apples CPU/GPU point",
+            "cpu": {"value": cpu["value"], "unit": "updates/s", "cores": procs, "kind": cpu["kind"],
+                    "single_thread_value": cpu["single_thread_value"], "replications": procs, "wall_s": cpu["wall_s"],
+                    "mean_success_pct": 100.0 * cpu["mean_success"] / FULL_NUE},
+            "gpu": {"value": gpu_val, "unit": "updates/s", "replications": reps, "kernel_ms": kms,
+                    "mean_success_pct": 100.0 * float(st["nSuccess"].mean()) / FULL_NUE},
+            "ratio_gpu_over_cpu_all_cores": gpu_val / cpu["value"],
+            "ratio_gpu_over_cpu_one_core": gpu_val / cpu["single_thread_value"]}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,6 +254,7 @@ def run_our_arm(args):
         per_gpu = value / world
         achieved = per_gpu * ALGO_BYTES_PER_UPDATE / 1e9
         traffic = measured_traffic()
+        same_workload = bool(traffic) and args.nue == 100000 and args.reps == 4096 and args.distribution == "beta" and args.scaling == "weak"
         line = {"metric": METRIC, "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -242,19 +276,30 @@ def run_our_arm(args):
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak,
-                             "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                             "traffic": traffic["dram_bytes_per_launch"] if same_workload else None,
                              "note": "achieved = updates/s/GPU x 32 B (SURVEY 8d contract); the engine is event-driven and "
                                      "moves fewer bytes than that model, so frac > 1 means avoided traffic -- see "
                                      "`traffic` (ncu dram bytes per launch) and DESIGN.md section 5; peak " + peak_src}}
-        if traffic and args.nue == 100000 and args.reps == 4096 and args.distribution == "beta":
-            # the same kernel against the bytes it REALLY moves (ncu dram__bytes per launch of this workload)
-            real = traffic["dram_bytes_per_launch"] / (kernel_ms / args.steps / 1e3) / 1e9
-            line["roofline_measured_traffic"] = {"bound": "hbm", "achieved": real, "peak": peak, "unit": "GB/s",
-                                                 "frac": real / peak,
-                                                 "note": "ncu dram bytes per launch / CUDA-event kernel time: the kernel is "
-                                                         "latency-bound at a balanced pipe mix, not DRAM-bound (profiles/r01d_ncu_128x8.md)"}
+        # the same kernel against the bytes it REALLY moves.  Counted live by the engine in this very run: every calendar
+        # record it read at its event time (ra_stats.recordMoves), 16 B in + 16 B out each; next to it the DRAM bytes ncu
+        # measured for this workload (profiles/traffic.json, written by tools/ncu_onepager.py from a capture of this round)
+        moved = 32.0 * tot["recordMoves"] * args.steps / world            # bytes per GPU over the timed region
+        real = moved / (kernel_ms / 1e3) / 1e9
+        line["roofline_measured_traffic"] = {
+            "bound": "hbm", "achieved": real, "peak": peak, "unit": "GB/s", "frac": real / peak,
+            "bytes_per_launch_counted_live": 32.0 * tot["recordMoves"] / world,
+            "bytes_per_launch_ncu": traffic["dram_bytes_per_launch"] if same_workload else None,
+            "note": "achieved = engine-counted record traffic of this run (recordMoves x 32 B) / CUDA-event kernel time; the "
+                    "event-driven engine moves a 16-B record only when a UE has an event, so this is the physical HBM "
+                    "fraction.  The kernel is issue/latency-bound, not DRAM-bound (profiles/r02*_ncu_w*.md)"}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_sample(args.nue, 1500, os.cpu_count() or 1)
+            procs = os.cpu_count() or 1
+            cb = cpu_reference_sample(args.nue, SAMPLE_MS, procs)         # the same sample the --impl reference arm times
+            cb["what"] = ("`value` = prefix sample at the headline size (same sample as the --impl reference arm); "
+                          "`full_replication` = complete replications at %d UEs on both CPU and GPU" % FULL_NUE)
+            if not args.no_full_replication:
+                cb["full_replication"] = full_replication_pair(pkg, local, procs)
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
@@ -274,6 +319,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-replication", action="store_true", help="skip the ~1-2 min complete-replication CPU/GPU pair")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

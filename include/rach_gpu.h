@@ -96,6 +96,8 @@ typedef struct ra_stats {
     long long collisionScans;    /* B:41,349  (B counts one per collided scan)                 */
     long long totalScans;        /* B:42,334,351 (one per scan)                                */
     long long updates;           /* nUE * ceil(simTimeMs / accessTime): the throughput unit    */
+    long long recordMoves;       /* engine bookkeeping (variant W): 16-byte calendar records read at their event time =
+                                    records written earlier; x 32 B = the state bytes the replication really moved  */
 } ra_stats;
 
 /* Engine options (all zero = defaults).

