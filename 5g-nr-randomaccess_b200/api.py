@@ -51,7 +51,9 @@ class RaOptions(C.Structure):
                 ("phaseTimers", C.c_int), ("reserved", C.c_int * 4)]
 
 
-SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_last_create_code", "ra_sim_run", "ra_sim_stats",
+DUMP_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(RaStats), C.POINTER(C.c_int))
+
+SYMBOLS = ["ra_sim_create", "ra_sim_create_ex", "ra_last_create_error", "ra_last_create_code", "ra_sim_run", "ra_sim_run_stream", "ra_sim_stats",
            "ra_sim_stats_all", "ra_sim_dump_ues", "ra_sim_geometry", "ra_sim_gains", "ra_sim_kernel_ms",
            "ra_sim_gpu_launches", "ra_sim_phase_cycles", "ra_sim_destroy", "ra_sim_last_error", "ra_params_default",
            "ra_horizon_ms", "ra_arrival_schedule", "ra_params_validate", "ra_version"]
@@ -80,6 +82,7 @@ def load_lib():
                                      C.POINTER(RaOptions)]
     lib.ra_last_create_error.restype = C.c_char_p
     lib.ra_sim_run.argtypes = [vp]
+    lib.ra_sim_run_stream.argtypes = [vp, DUMP_CB, vp]
     lib.ra_sim_stats.argtypes = [vp, C.c_int, C.c_int, C.POINTER(RaStats)]
     lib.ra_sim_stats_all.argtypes = [vp, vp]
     lib.ra_sim_dump_ues.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -154,6 +157,24 @@ class RachSim:
 
     def run(self):
         self._check(self._lib.ra_sim_run(self._h))
+        return self
+
+    def run_stream(self, on_replication):
+        """ra_sim_run_stream: on_replication(point, rep, stats_dict, rows[nUE, 16]) is called for every replication as
+        soon as it has finished on the GPU (completion order), while the kernel keeps running.  Needs dump_ues=True."""
+        err = []
+
+        def _cb(_user, point, rep, st, rows):
+            try:
+                n = self.points[point].nUE
+                arr = np.ctypeslib.as_array(rows, shape=(n * RA_DUMP_FIELDS,)).reshape(n, RA_DUMP_FIELDS).copy()
+                on_replication(point, rep, st.contents.as_dict(), arr)
+            except Exception as e:      # never unwind through the C frames
+                err.append(e)
+        cb = DUMP_CB(_cb)
+        self._check(self._lib.ra_sim_run_stream(self._h, cb, None))
+        if err:
+            raise err[0]
         return self
 
     def stats(self, point=0, rep=0):

@@ -105,7 +105,7 @@ struct RaPointDev {
     /* byte offsets of the block's tables in dynamic shared memory (ra_layout): a function of (R, P) only, kept
      * here so that a launch whose replications share one point reads them as kernel constants */
     unsigned oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore, oExtraFirst, oClsSize;
-    unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes;
+    unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes, oDead, padO;
     /* rand() % backoffIndicator (W:514,540,685), rand() % nPreamble (W:478,502,701), subTime % accessTime (W:518) */
     RA_HDM unsigned modBI(unsigned x) const { return ra_mod(x, (unsigned)BI, magicBI); }
     RA_HDM unsigned modP(unsigned x) const { return ra_mod(x, (unsigned)P, magicP); }
@@ -115,7 +115,7 @@ struct RaPointDev {
 /* table layout for (R, P); 16-byte records first.  One definition for the runtime point (ra_layout) and for the
  * compile-time view below. */
 struct RaLayout {
-    unsigned oSLand, oSUnc, oSLandMeta, oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore,
+    unsigned oSLand, oSUnc, oSLandMeta, oMinI, oCnt, oBcount, oDead, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore,
              oExtraFirst, oClsSize, oHist, oSIdx, smemBytes;
 };
 #define RA_LAYOUT_BODY(R_, P_) \
@@ -126,6 +126,7 @@ struct RaLayout {
     l.oMinI = o;       o += 4u * RP; \
     l.oCnt = o;        o += 4u * RP; \
     l.oBcount = o;     o += 4u * (unsigned)(R_); \
+    l.oDead = o;       o += 4u * (unsigned)(R_); \
     l.oM3count = o;    o += 4u * RA_M3RING; \
     l.oN = o;          o += P4; \
     l.oL1 = o;         o += P4; \
@@ -154,7 +155,7 @@ struct RaPointFixed : RaPointDev {
     static constexpr int P = P_, BI = BI_, A = A_, Wn = Wn_, R = R_;
     static constexpr RaLayout L = ra_layout_of(R_, P_);
     static constexpr unsigned oSLand = L.oSLand, oSUnc = L.oSUnc, oSLandMeta = L.oSLandMeta, oMinI = L.oMinI, oCnt = L.oCnt,
-        oBcount = L.oBcount, oM3count = L.oM3count, oN = L.oN, oL1 = L.oL1, oNlList = L.oNlList, oL1m = L.oL1m, oL2 = L.oL2,
+        oBcount = L.oBcount, oDead = L.oDead, oM3count = L.oM3count, oN = L.oN, oL1 = L.oL1, oNlList = L.oNlList, oL1m = L.oL1m, oL2 = L.oL2,
         oBefore = L.oBefore, oExtraFirst = L.oExtraFirst, oClsSize = L.oClsSize, oHist = L.oHist, oSIdx = L.oSIdx,
         smemBytes = L.smemBytes;
     RA_HDM unsigned modBI(unsigned x) const { return x % (unsigned)BI_; }
@@ -255,11 +256,12 @@ static inline unsigned char* ra_smem() { return ra_emu_smem_base; }
 #endif
 #define RA_TAB_U(off)  (reinterpret_cast<unsigned*>(ra_smem() + (off)))
 #define RA_TAB_Q(off)  (reinterpret_cast<uint4*>(ra_smem() + (off)))
-struct RaTabsT { unsigned *minI, *cnt, *bcount, *m3count, *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize, *hist, *sIdx, *sLandMeta; uint4 *sLand, *sUnc; };
+struct RaTabsT { unsigned *minI, *cnt, *bcount, *dead, *m3count, *N, *l1, *nlList, *l1m, *l2, *before, *extraFirst, *clsSize, *hist, *sIdx, *sLandMeta; uint4 *sLand, *sUnc; };
 #define RA_T(name, O) (reinterpret_cast<decltype(RaTabsT::name)>(ra_smem() + pt.O))
 #define S_minI       RA_T(minI, oMinI)             /* [R*P] lowest UE index of the cohort                        */
 #define S_cnt        RA_T(cnt, oCnt)               /* [R*P] cohort size                                          */
 #define S_bcount     RA_T(bcount, oBcount)         /* [R]   records in each move bucket                          */
+#define S_dead       RA_T(dead, oDead)             /* [R]   ... of which granted away since (left as RA_DEAD records) */
 #define S_m3count    RA_T(m3count, oM3count)       /* [RA_M3RING]                                                */
 #define S_N          RA_T(N, oN)                   /* [P] each, N .. clsSize                                     */
 #define S_l1         RA_T(l1, oL1)
@@ -278,7 +280,7 @@ struct RaTabsT { unsigned *minI, *cnt, *bcount, *m3count, *N, *l1, *nlList, *l1m
 RA_HD void ra_layout(RaPointDev& pt) {
     const RaLayout l = ra_layout_of(pt.R, pt.P);
     pt.oSLand = l.oSLand; pt.oSUnc = l.oSUnc; pt.oSLandMeta = l.oSLandMeta; pt.oMinI = l.oMinI; pt.oCnt = l.oCnt;
-    pt.oBcount = l.oBcount; pt.oM3count = l.oM3count; pt.oN = l.oN; pt.oL1 = l.oL1; pt.oNlList = l.oNlList;
+    pt.oBcount = l.oBcount; pt.oDead = l.oDead; pt.oM3count = l.oM3count; pt.oN = l.oN; pt.oL1 = l.oL1; pt.oNlList = l.oNlList;
     pt.oL1m = l.oL1m; pt.oL2 = l.oL2; pt.oBefore = l.oBefore; pt.oExtraFirst = l.oExtraFirst; pt.oClsSize = l.oClsSize;
     pt.oHist = l.oHist; pt.oSIdx = l.oSIdx; pt.smemBytes = l.smemBytes;
 }
@@ -380,7 +382,7 @@ template <bool DUMP, class PT>
 RA_HD void ra_job_init(const RaJobT<PT>& job, RaShared& s, int tid, int nt) {
     const PT& pt = *job.pt;
     for (int i = tid; i < pt.R * pt.P; i += nt) { S_cnt[i] = 0; S_minI[i] = RA_INF32; }
-    for (int i = tid; i < pt.R; i += nt) S_bcount[i] = 0;
+    for (int i = tid; i < pt.R; i += nt) { S_bcount[i] = 0; S_dead[i] = 0; }
     for (int i = tid; i < RA_M3RING; i += nt) S_m3count[i] = 0;
     for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0;
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
@@ -424,6 +426,9 @@ RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt)
         }
         s.nArr = s.activeCheck - s.acOld;
         s.nMov = S_bcount[(unsigned)T & Rm];
+        /* every record of the bucket was granted before its window expired (the normal case under light load: the
+         * first scan of a lone UE is answered): nothing to read, nothing to move */
+        if (S_dead[(unsigned)T & Rm] == s.nMov) s.nMov = 0;
         s.nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
         s.recMoves += (ra_u64)s.nMov + s.nM3;
     }
@@ -753,6 +758,7 @@ RA_HD void ra_grant_nonmover(const RaJobT<PT>& job, const RaWork& w, RaShared& s
     const PT& pt = *job.pt;
     uint4 rec = w.bucket[at];
     w.bucket[at].x = RA_DEAD;
+    RA_AADD(&S_dead[slot], 1u);
     S_cnt[slot * pt.P + q] -= 1; S_minI[slot * pt.P + q] = RA_INF32;   /* it was alone in its class */
     if (DUMP) {
         int* row = job.dump + (size_t)rec.x * RA_DUMP_W;
@@ -784,7 +790,7 @@ RA_HD void ra_phase6_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, i
 #endif
             { unsigned k = RA_AADD(&s.nNl, 1u); S_nlList[k] = q; }      /* rare: found by ra_phase6b */
         }
-        if (q == 0) { S_bcount[(unsigned)T & Rm] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
+        if (q == 0) { S_bcount[(unsigned)T & Rm] = 0; S_dead[(unsigned)T & Rm] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
         /* the cohort that moved in this ms is gone */
         S_cnt[((unsigned)T & Rm) * pt.P + q] = 0; S_minI[((unsigned)T & Rm) * pt.P + q] = RA_INF32;
         return;

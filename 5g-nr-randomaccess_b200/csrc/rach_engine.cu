@@ -72,6 +72,7 @@ struct RaKernelArgs {
     ra_stats*         stats;        /* [nJobs]                                   */
     int*              dump;         /* [nJobs][dumpStride] or NULL               */
     int*              errFlag;
+    volatile int*     doneFlags;    /* [nJobs] host-mapped: 1 = the replication's stats and dump rows are complete (streaming), or NULL */
     ra_u64*           phaseCycles;  /* [RA_NPHASE] cycles of thread 0 per phase, summed over blocks */
     size_t            dumpStride;
     int               nJobs, maxP, maxR;
@@ -219,6 +220,8 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             st.recordMoves = (long long)s.recMoves;
             a.stats[jobId] = st;
             if (s.overflow) atomicExch(a.errFlag, s.overflow);
+            /* every thread's dump rows were written before the barrier above; publish them system-wide, then the flag */
+            if (a.doneFlags) { __threadfence_system(); a.doneFlags[jobId] = 1; }
         }
     }
     __syncthreads();
@@ -309,6 +312,10 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
             a.stats[jobId] = st;
             if (s.overflow) atomicExch(a.errFlag, s.overflow);
         }
+        if (a.doneFlags) {                                  /* the dump rows of every thread, then the flag */
+            __syncthreads();
+            if (tid == 0) { __threadfence_system(); a.doneFlags[jobId] = 1; }
+        }
     }
 }
 
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(32) ra_u0_kernel(RaKernelArgs a, int cap, int 
         o.updates = (long long)pt->nUE * (long long)((st.simTime + 4) / 5);
         a.stats[jobId] = o;
         if (st.overflow) atomicExch(a.errFlag, st.overflow);
+        if (a.doneFlags) { __threadfence_system(); a.doneFlags[jobId] = 1; }      /* after the __syncwarp() above */
     }
 }
 
@@ -399,6 +407,9 @@ struct RaDev {
     cudaStream_t stream = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<ra_stats> hStats;
     int hErr = 0;
+    /* streaming of per-UE dumps while the kernel runs (ra_sim_run_stream) */
+    int* hDone = nullptr;             /* [nJobs] pinned, mapped: written by the kernel                   */
+    cudaStream_t copyStream = nullptr;
 };
 
 /* shape: 0 = 128 x 8, 1 = 256 x 5, 2 = 512 x 2 (threads x resident blocks per SM) */
@@ -447,6 +458,8 @@ static void ra_free_dev(RaDev& d) {
     if (d.e0) cudaEventDestroy(d.e0);
     if (d.e1) cudaEventDestroy(d.e1);
     if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copyStream) cudaStreamDestroy(d.copyStream);
+    if (d.hDone) cudaFreeHost(d.hDone);
 }
 
 static size_t ra_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -686,7 +699,7 @@ extern "C" ra_sim* ra_sim_create(const ra_params* points, int nPoints, int repsP
 }
 
 /* launch on one device (asynchronous); the caller synchronises */
-static int ra_launch_device(ra_sim* sim, RaDev& d) {
+static int ra_launch_device(ra_sim* sim, RaDev& d, bool stream = false) {
     const int nJobs = (int)d.jobs.size();
     RA_CUDA(sim, cudaSetDevice(d.id));
     RA_CUDA(sim, cudaMemsetAsync(d.dCounter, 0, sizeof(unsigned), d.stream));
@@ -696,6 +709,16 @@ static int ra_launch_device(ra_sim* sim, RaDev& d) {
     a.points = d.dPoints; a.jobPoint = d.dJobPoint; a.jobRep = d.dJobRep; a.works = d.dWorks;
     a.jobCounter = d.dCounter; a.stats = d.dStats; a.dump = d.dDump; a.errFlag = d.dErr; a.phaseCycles = sim->opt.phaseTimers ? d.dCyc : nullptr;
     a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
+    if (stream) {
+        if (!d.hDone) {
+            RA_CUDA(sim, cudaHostAlloc(&d.hDone, sizeof(int) * (size_t)nJobs, cudaHostAllocMapped));
+            RA_CUDA(sim, cudaStreamCreateWithFlags(&d.copyStream, cudaStreamNonBlocking));
+        }
+        memset(d.hDone, 0, sizeof(int) * (size_t)nJobs);
+        int* dv = nullptr;
+        RA_CUDA(sim, cudaHostGetDevicePointer(&dv, d.hDone, 0));
+        a.doneFlags = dv;
+    }
     RA_CUDA(sim, cudaEventRecord(d.e0, d.stream));
     a.worksN = d.dWorksN;
     a.gainDump = d.dGainDump; a.gainStride = (size_t)sim->cap;
@@ -761,6 +784,95 @@ extern "C" int ra_sim_run(ra_sim* sim) {
             cudaSetDevice(d.id); cudaStreamSynchronize(d.stream);
         }
     }
+    if (rc != RA_OK) { sim->err = firstErr; return rc; }
+    sim->kernelMs = ms; sim->ran = true;
+    return RA_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-UE logs at scale (the role of saveResult, RandomAccessWithNOMA.c:797-825, for thousands of replications): the step
+ * kernel never waits for the host.  Each replication raises a flag in host-mapped memory when its counters and its
+ * nUE x 16 dump rows are complete; this thread polls the flags while the kernel keeps running, copies finished
+ * replications out with one cudaMemcpyAsync each on a second stream into a ring of pinned staging buffers, and hands
+ * them to the callback in completion order.
+ * ------------------------------------------------------------------------------------------ */
+#include <unistd.h>
+extern "C" int ra_sim_run_stream(ra_sim* sim, ra_dump_cb cb, void* user) {
+    if (!sim || !cb) return RA_E_INVAL;
+    if (!sim->opt.dumpUEs) { sim->err = "ra_sim_run_stream needs ra_options.dumpUEs = 1 at create time"; return RA_E_STATE; }
+    sim->launches = 0; sim->ran = false;
+    const int kSlots = 4;
+    struct Slot { int* rows = nullptr; ra_stats* st = nullptr; cudaEvent_t ev = nullptr; int dev = -1, job = -1; };
+    std::vector<Slot> slots(kSlots);
+    int rc = RA_OK;
+    std::string firstErr;
+    auto fail = [&](int code, const std::string& msg) { if (rc == RA_OK) { rc = code; firstErr = msg; } };
+    for (Slot& sl : slots) {
+        if (cudaHostAlloc(&sl.rows, sizeof(int) * sim->dumpStride, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&sl.st, sizeof(ra_stats), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) { fail(RA_E_NOMEM, "pinned staging buffers for the dump stream"); break; }
+    }
+    std::vector<char> launched(sim->devs.size(), 0);
+    for (size_t k = 0; k < sim->devs.size() && rc == RA_OK; ++k) {
+        RaDev& d = sim->devs[k];
+        if (d.jobs.empty()) continue;
+        d.hErr = 0;
+        launched[k] = 1;
+        const int lrc = ra_launch_device(sim, d, true);
+        if (lrc == RA_OK) sim->launches++; else fail(lrc, sim->err);
+    }
+    if (rc == RA_OK) {
+        size_t total = 0, delivered = 0;
+        std::vector<std::vector<char>> issued(sim->devs.size());
+        for (size_t k = 0; k < sim->devs.size(); ++k) { issued[k].assign(sim->devs[k].jobs.size(), 0); total += sim->devs[k].jobs.size(); }
+        int head = 0, inflight = 0;                        /* slots [head, head + inflight) hold copies in issue order */
+        while (delivered < total && rc == RA_OK) {
+            bool progress = false;
+            for (size_t k = 0; k < sim->devs.size() && inflight < kSlots; ++k) {
+                RaDev& d = sim->devs[k];
+                for (size_t j = 0; j < d.jobs.size() && inflight < kSlots; ++j) {
+                    if (issued[k][j] || !((volatile int*)d.hDone)[j]) continue;
+                    Slot& sl = slots[(head + inflight) % kSlots];
+                    const int point = d.jobs[j] / sim->reps;
+                    cudaSetDevice(d.id);
+                    cudaError_t e1 = cudaMemcpyAsync(sl.rows, d.dDump + j * sim->dumpStride,
+                                                     sizeof(int) * (size_t)sim->points[point].nUE * RA_DUMP_W, cudaMemcpyDeviceToHost, d.copyStream);
+                    cudaError_t e2 = cudaMemcpyAsync(sl.st, d.dStats + j, sizeof(ra_stats), cudaMemcpyDeviceToHost, d.copyStream);
+                    cudaError_t e3 = cudaEventRecord(sl.ev, d.copyStream);
+                    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fail(RA_E_CUDA, "dump stream copy failed"); break; }
+                    sl.dev = (int)k; sl.job = (int)j; issued[k][j] = 1; ++inflight; progress = true;
+                }
+            }
+            while (inflight > 0 && rc == RA_OK) {
+                Slot& sl = slots[head];
+                const cudaError_t q = cudaEventQuery(sl.ev);
+                if (q == cudaErrorNotReady) break;
+                if (q != cudaSuccess) { fail(RA_E_CUDA, std::string("dump stream: ") + cudaGetErrorString(q)); break; }
+                const int gj = sim->devs[sl.dev].jobs[sl.job];
+                cb(user, gj / sim->reps, gj % sim->reps, sl.st, sl.rows);
+                head = (head + 1) % kSlots; --inflight; ++delivered; progress = true;
+            }
+            if (!progress && rc == RA_OK) {
+                /* nothing finished since the last look: make sure the kernels are still healthy, then wait a little */
+                for (size_t k = 0; k < sim->devs.size(); ++k) {
+                    if (!launched[k]) continue;
+                    const cudaError_t q = cudaStreamQuery(sim->devs[k].stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) fail(RA_E_CUDA, std::string("step kernel: ") + cudaGetErrorString(q));
+                }
+                usleep(200);
+            }
+        }
+    }
+    double ms = 0;
+    for (size_t k = 0; k < sim->devs.size(); ++k) {         /* drain every launched device, also after an error */
+        if (!launched[k]) continue;
+        RaDev& d = sim->devs[k];
+        cudaSetDevice(d.id);
+        if (d.copyStream) cudaStreamSynchronize(d.copyStream);
+        if (rc == RA_OK) { const int crc = ra_collect_device(sim, d, &ms); if (crc != RA_OK) fail(crc, sim->err); }
+        else cudaStreamSynchronize(d.stream);
+    }
+    for (Slot& sl : slots) { if (sl.rows) cudaFreeHost(sl.rows); if (sl.st) cudaFreeHost(sl.st); if (sl.ev) cudaEventDestroy(sl.ev); }
     if (rc != RA_OK) { sim->err = firstErr; return rc; }
     sim->kernelMs = ms; sim->ran = true;
     return RA_OK;

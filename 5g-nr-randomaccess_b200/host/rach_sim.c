@@ -20,6 +20,12 @@
  *           --nue a,b,c  (points; default the reference sweep 10000..100000 step 10000, W:221)
  *           --no-logs    (skip the per-UE *_Logs.txt, W:797-825)
  *           --outdir DIR (default "."), --device N, --seed64 S (tape key, default 0)
+ *           --devices a,b,c  shard the (point, seed) list over several GPUs of the box (ra_sim_create devices[])
+ *           --binlog     per-UE logs as compact binary instead of text: <seed>_<P>_UE<nUE>_Logs.bin = 32-byte header
+ *                        ("RAUELOG1", int32 nUE, nFields = 14, seed, nPreamble, 0, 0) + nUE x 14 int32, the fields
+ *                        saveResult prints after Idx (W:812-819), 56 B per UE instead of ~240 B of text
+ *   The per-UE logs are written WHILE the kernel runs (ra_sim_run_stream): each finished replication is copied out
+ *   asynchronously and written by the host thread; the report itself is printed afterwards in the reference's order.
  *
  * Differences that cannot be hidden: randomness is the Philox draw tape keyed by
  * (seed64, replication = the reference's randomSeed, UE, ms), not libc rand(); the whole sweep
@@ -151,6 +157,54 @@ static int report_u0(const ra_params* base, const int* nueList, int nNue, const 
     return 0;
 }
 
+/* ---- per-UE logs, written from the streaming callback (completion order) ------------------------------------- */
+typedef struct {
+    const ra_params* pts; int times; const char* dir; char format; int uniform, binlog;
+    float* totalDelay;          /* [point * times + seed]: float accumulation in UE order, W:338,346 */
+    int failed;
+} log_ctx;
+
+static void log_cb(void* user, int point, int seed, const ra_stats* st, const int* ue) {
+    log_ctx* c = (log_ctx*)user;
+    (void)st;
+    const int nUE = c->pts[point].nUE, nPreamble = c->pts[point].nPreamble;
+    float totalDelay = 0;
+    for (int i = 0; i < nUE; ++i) if (ue[i * RA_DUMP_FIELDS + 13] == 1) totalDelay += (float)ue[i * RA_DUMP_FIELDS + 0];
+    c->totalDelay[(size_t)point * c->times + seed] = totalDelay;
+    if (c->format == 'n') return;
+    char path[800];
+    if (c->binlog) {
+        snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.bin", c->dir, seed, nPreamble, nUE);
+        FILE* fp = fopen(path, "wb");
+        if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); c->failed = 1; return; }
+        int hdr[8] = {0, 0, nUE, 14, seed, nPreamble, 0, 0};
+        memcpy(hdr, "RAUELOG1", 8);
+        fwrite(hdr, sizeof hdr, 1, fp);
+        int* row = (int*)malloc(sizeof(int) * 14 * 4096);
+        for (int i0 = 0; i0 < nUE; i0 += 4096) {
+            const int n = nUE - i0 < 4096 ? nUE - i0 : 4096;
+            for (int i = 0; i < n; ++i) memcpy(row + i * 14, ue + (size_t)(i0 + i) * RA_DUMP_FIELDS, sizeof(int) * 14);
+            fwrite(row, sizeof(int) * 14, (size_t)n, fp);
+        }
+        free(row);
+        fclose(fp);
+        return;
+    }
+    if (c->format == 'b' && c->uniform) snprintf(path, sizeof path, "%s/%d_Exclude_msg2_failures_UE%05d_Logs.txt", c->dir, nPreamble, nUE);   /* B:488 */
+    else snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.txt", c->dir, seed, nPreamble, nUE);      /* W:797-825 */
+    FILE* fp = fopen(path, "w+");
+    if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); c->failed = 1; return; }
+    static const char* names[15] = {"Idx", "Timer", "Active", "txTime", "FirstTxTime", "SecondTxTime", "NowBackoff",
+        "Preamble", "Preamble change", "RAR window", "Max RAR", "Preamble reTx", "MSG 2 Flag", "ConnectRequest", "MSG 4 Flag"};
+    for (int i = 0; i < nUE; ++i) {
+        const int* r = ue + (size_t)i * RA_DUMP_FIELDS;
+        fprintf(fp, "%s: %d", names[0], i);
+        for (int f = 0; f < 14; ++f) fprintf(fp, " | %s: %d", names[f + 1], r[f]);
+        fputc('\n', fp);
+    }
+    fclose(fp);
+}
+
 static int is_flag(const char* a, const char* l, const char* s, const char* alias) {
     return strcmp(a, l) == 0 || strcmp(a, s) == 0 || (alias && strcmp(a, alias) == 0);
 }
@@ -158,7 +212,8 @@ static int is_flag(const char* a, const char* l, const char* s, const char* alia
 int main(int argc, char* argv[]) {
     ra_params base;
     ra_params_default(&base, RA_VARIANT_W);
-    int times = 1, writeLogs = 1, device = 0, grantSet = 0, preambleSet = 0, backoffSet = 0;
+    int times = 1, writeLogs = 1, device = 0, grantSet = 0, preambleSet = 0, backoffSet = 0, binlog = 0;
+    int devList[64], nDev = 0;
     char format = 'w';
     const char* outdir = ".";
     int nueList[64], nNue = 0;
@@ -167,6 +222,7 @@ int main(int argc, char* argv[]) {
     for (int i = 1; i < argc; i += 2) {
         const char* a = argv[i];
         if (strcmp(a, "--no-logs") == 0) { writeLogs = 0; i -= 1; continue; }
+        if (strcmp(a, "--binlog") == 0) { binlog = 1; i -= 1; continue; }
         const char* v = (i + 1 < argc) ? argv[i + 1] : "";      /* the reference dereferences argv[i+1] blindly (W:94) */
         if (is_flag(a, "--times", "-t", NULL)) {
             if (atoi(v) < 1) die("Simulation count must be greater than zero.");
@@ -208,10 +264,15 @@ int main(int argc, char* argv[]) {
         } else if (strcmp(a, "--format") == 0) { format = v[0];
         } else if (strcmp(a, "--outdir") == 0) { outdir = v;
         } else if (strcmp(a, "--device") == 0) { device = atoi(v);
+        } else if (strcmp(a, "--devices") == 0) {
+            char* dup = strdup(v);
+            for (char* tok = strtok(dup, ","); tok && nDev < 64; tok = strtok(NULL, ",")) devList[nDev++] = atoi(tok);
+            free(dup);
         } else if (strcmp(a, "--seed64") == 0) { seed64 = strtoull(v, NULL, 0);
         } else usage_and_exit();
     }
     if (nNue == 0) for (int n = 10000; n <= 100000; n += 10000) nueList[nNue++] = n;   /* W:221 */
+    if (nDev == 0) devList[nDev++] = device; else device = devList[0];
     base.seed = seed64;
     if (format != 'w' && format != 'b' && format != 'n' && format != 'u') usage_and_exit();
     if (format == 'u') return report_u0(&base, nueList, nNue, outdir, writeLogs, device, preambleSet, backoffSet);
@@ -237,9 +298,15 @@ int main(int argc, char* argv[]) {
     for (int k = 0; k < nNue; ++k) { pts[k] = base; pts[k].nUE = nueList[k]; }
     ra_options opt; memset(&opt, 0, sizeof opt);
     opt.dumpUEs = writeLogs;
-    ra_sim* sim = ra_sim_create_ex(pts, nNue, times, &device, 1, &opt);
+    ra_sim* sim = ra_sim_create_ex(pts, nNue, times, devList, nDev, &opt);
     if (!sim) { fprintf(stderr, "rach_sim: %s\n", ra_last_create_error()); return 2; }
-    if (ra_sim_run(sim) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+    log_ctx lc; memset(&lc, 0, sizeof lc);
+    lc.pts = pts; lc.times = times; lc.dir = dir; lc.format = format; lc.uniform = uniform; lc.binlog = binlog;
+    lc.totalDelay = (float*)calloc((size_t)nNue * (size_t)times, sizeof(float));
+    /* with logs: every replication is copied out and written while the kernel is still running */
+    const int rrc = writeLogs ? ra_sim_run_stream(sim, log_cb, &lc) : ra_sim_run(sim);
+    if (rrc != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
+    if (lc.failed) return 2;
 
     for (int seed = 0; seed < times; ++seed) {                   /* W:216 */
         for (int k = 0; k < nNue; ++k) {                         /* W:221 */
@@ -256,15 +323,9 @@ int main(int argc, char* argv[]) {
             const int nAccessUE = arr[0];
             free(arr);
 
-            int* ue = NULL;
-            float totalDelay = 0;                                /* float accumulation in UE order, W:338,346 */
-            if (writeLogs) {
-                ue = (int*)malloc(sizeof(int) * (size_t)nUE * RA_DUMP_FIELDS);
-                if (ra_sim_dump_ues(sim, k, seed, ue) != RA_OK) { fprintf(stderr, "rach_sim: %s\n", ra_sim_last_error(sim)); return 2; }
-                for (int i = 0; i < nUE; ++i) if (ue[i * RA_DUMP_FIELDS + 13] == 1) totalDelay += (float)ue[i * RA_DUMP_FIELDS + 0];
-            } else {
-                totalDelay = (float)st.delaySum;                 /* identical while the sum stays below 2^24 */
-            }
+            /* float accumulation in UE order, W:338,346 (from the streamed rows); without logs the integer sum, which is
+             * identical while it stays below 2^24 */
+            const float totalDelay = writeLogs ? lc.totalDelay[(size_t)k * times + seed] : (float)st.delaySum;
             if (format == 'n') {                                 /* NOMA.c:598-635 */
                 char path[800];
                 snprintf(path, sizeof path, "%s/Sector_%d_Result.txt", dir, nUE);
@@ -275,7 +336,6 @@ int main(int argc, char* argv[]) {
                          ((float)(int)st.preambleTxSum / (float)st.nSuccess), ((float)(int)st.delaySum / (float)st.nSuccess));
                 fputs(line, stdout); fputs(line, fp);
                 fclose(fp);
-                free(ue);
                 if (k == nNue - 1) printf("Done\n");             /* NOMA.c:716 */
                 continue;
             }
@@ -317,25 +377,10 @@ int main(int argc, char* argv[]) {
             }
             fclose(fp);
 
-            if (writeLogs) {                                                             /* W:797-825 */
-                if (format == 'b' && uniform) snprintf(path, sizeof path, "%s/%d_Exclude_msg2_failures_UE%05d_Logs.txt", dir, nPreamble, nUE);   /* B:488 */
-                else snprintf(path, sizeof path, "%s/%d_%d_UE%05d_Logs.txt", dir, seed, nPreamble, nUE);
-                fp = fopen(path, "w+");
-                if (!fp) { fprintf(stderr, "rach_sim: cannot write %s: %s\n", path, strerror(errno)); return 2; }
-                static const char* names[15] = {"Idx", "Timer", "Active", "txTime", "FirstTxTime", "SecondTxTime", "NowBackoff",
-                    "Preamble", "Preamble change", "RAR window", "Max RAR", "Preamble reTx", "MSG 2 Flag", "ConnectRequest", "MSG 4 Flag"};
-                for (int i = 0; i < nUE; ++i) {
-                    const int* r = ue + (size_t)i * RA_DUMP_FIELDS;
-                    fprintf(fp, "%s: %d", names[0], i);
-                    for (int f = 0; f < 14; ++f) fprintf(fp, " | %s: %d", names[f + 1], r[f]);
-                    fputc('\n', fp);
-                }
-                fclose(fp);
-                free(ue);
-            }
         }
     }
-    fprintf(stderr, "rach_sim: %d points x %d seeds, kernel %.1f ms (%s)\n", nNue, times, ra_sim_kernel_ms(sim), ra_version());
+    fprintf(stderr, "rach_sim: %d points x %d seeds on %d device(s), kernel %.1f ms (%s)\n", nNue, times, nDev, ra_sim_kernel_ms(sim), ra_version());
+    free(lc.totalDelay);
     ra_sim_destroy(sim);
     free(pts);
     return 0;

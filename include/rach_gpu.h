@@ -125,6 +125,13 @@ const char* ra_last_create_error(void);
 int         ra_last_create_code(void);               /* RA_E_* of the last failed create on this thread, RA_OK otherwise */
 
 int         ra_sim_run(ra_sim* sim);                 /* blocking; may be called repeatedly */
+/* Per-UE logs at scale (saveResult W:797-825 for many replications): like ra_sim_run, and while the kernel is still
+ * running every finished replication is copied out (one asynchronous copy per replication on a second stream, pinned
+ * staging) and handed to `cb` -- in completion order, from the calling thread; `rows` (nUE x RA_DUMP_FIELDS ints, layout
+ * of ra_sim_dump_ues) and `st` are valid during the call only.  The step kernel never waits for the host.
+ * Needs ra_options.dumpUEs = 1.  ra_sim_stats / ra_sim_dump_ues work afterwards as after ra_sim_run. */
+typedef void (*ra_dump_cb)(void* user, int point, int rep, const ra_stats* st, const int* rows);
+int         ra_sim_run_stream(ra_sim* sim, ra_dump_cb cb, void* user);
 int         ra_sim_stats(ra_sim* sim, int point, int rep, ra_stats* out);
 int         ra_sim_stats_all(ra_sim* sim, ra_stats* out /* [nPoints*repsPerPoint] */);
 /* out[nUE * RA_DUMP_FIELDS]: idx-major, fields in saveResult order (W:812-819) after idx:

@@ -193,3 +193,34 @@ def test_format_u_matches_random_access_simulator_c(tmp_path, oracle):
     assert ours2 == exp
     name = "2_Exclude_msg2_failures_UE%05d_Logs.txt" % nues[1]
     assert (tmp_path / "ours" / "2_SimulationResults" / name).read_bytes() == (refs[1][0] / "2_SimulationResults" / name).read_bytes()
+
+
+def test_binary_logs_and_device_list(tmp_path):
+    """--binlog writes the 14 saveResult fields (W:812-819) per UE as int32 after a 32-byte header; the numbers equal the
+    text log's; --devices takes a list (all GPUs of the box) and changes nothing in the output."""
+    import re
+    import numpy as np
+    import torch
+    pkg = importlib.import_module("5g-nr-randomaccess_b200")
+    exe = pkg.build_host()
+    common = ["-t", "3", "--nue", "1200,5000", "-g", "5"]
+    subprocess.run([exe] + common + ["--outdir", str(tmp_path / "txt")], capture_output=True, text=True, check=True)
+    devs = ",".join(str(i) for i in range(torch.cuda.device_count()))
+    out_b = subprocess.run([exe] + common + ["--binlog", "--devices", devs, "--outdir", str(tmp_path / "bin")],
+                           capture_output=True, text=True, check=True)
+    assert ("on %d device(s)" % torch.cuda.device_count()) in out_b.stderr
+    for seed in range(3):
+        for nue in (1200, 5000):
+            raw = (tmp_path / "bin" / "NomaBetaResults" / ("%d_54_UE%05d_Logs.bin" % (seed, nue))).read_bytes()
+            assert raw[:8] == b"RAUELOG1"
+            hdr = np.frombuffer(raw[8:32], dtype="<i4")
+            assert list(hdr[:4]) == [nue, 14, seed, 54] and len(raw) == 32 + nue * 14 * 4
+            rows = np.frombuffer(raw[32:], dtype="<i4").reshape(nue, 14)
+            txt = (tmp_path / "txt" / "NomaBetaResults" / ("%d_54_UE%05d_Logs.txt" % (seed, nue))).read_text().splitlines()
+            assert len(txt) == nue
+            for i in (0, 1, nue // 2, nue - 1):
+                vals = [int(x) for x in re.findall(r": (-?\d+)", txt[i])]
+                assert vals[0] == i and vals[1:] == list(rows[i]), (seed, nue, i)
+            a = (tmp_path / "txt" / "NomaBetaResults" / ("%d_54_%d_Results.txt" % (seed, nue))).read_bytes()
+            b = (tmp_path / "bin" / "NomaBetaResults" / ("%d_54_%d_Results.txt" % (seed, nue))).read_bytes()
+            assert a == b

@@ -209,6 +209,31 @@ def test_batch_is_placement_invariant(pkg, oracle):
     assert len({int(x) for x in allst[0]["delaySum"]}) > 20      # replications really differ
 
 
+def test_streamed_dumps_equal_the_blocking_ones(pkg):
+    """ra_sim_run_stream (per-UE logs at scale, the role of saveResult W:797-825): every replication is delivered exactly
+    once, while the kernel runs, with the rows ra_sim_dump_ues returns afterwards -- for all three engines."""
+    for variant, pts, reps in ((0, [pkg.default_params(nUE=6000, seed=3), pkg.default_params(nUE=2500, seed=4, nPreamble=8)], 300),
+                               (2, [pkg.default_params(variant=2, nUE=5000, seed=5)], 64),
+                               (1, [pkg.default_params(variant=1, nUE=20000, seed=6)], 40)):
+        got = {}
+
+        def on_rep(point, rep, st, rows):
+            assert (point, rep) not in got
+            got[(point, rep)] = (st, rows)
+        with pkg.RachSim(pts, reps=reps, devices=[0], rep_offset=9, dump_ues=True) as sim:
+            sim.run_stream(on_rep)
+            assert len(got) == len(pts) * reps
+            allst = sim.stats_all()
+            for (point, rep) in [(0, 0), (len(pts) - 1, reps - 1), (0, reps // 2)]:
+                st, rows = got[(point, rep)]
+                np.testing.assert_array_equal(rows, sim.dump_ues(point, rep))
+                for k in ("simTimeMs", "nSuccess", "preambleTxSum", "delaySum"):
+                    assert st[k] == int(allst[point, rep][k]), (variant, k)
+            first = sim.stats_all().copy()
+            sim.run()                                   # the plain run after a streamed one gives the same counters
+            assert (sim.stats_all() == first).all()
+
+
 def test_error_paths(pkg):
     with pytest.raises(pkg.RachError, match="nPreamble"):
         pkg.RachSim([pkg.default_params(nPreamble=0)], reps=1)
