@@ -74,7 +74,7 @@ def test_readme_tables_with_confidence_intervals():
     buf = io.StringIO()
     res = _ap().readme_tables(seeds=16, out=buf)
     txt = buf.getvalue()
-    assert txt.count("#### Retransmission limit") == 3 and txt.count("+-") == 3 * 4 * 10
+    assert txt.count("#### Retransmission limit") == 3 and txt.count(" +- ") == 3 * 4 * 10 + 3      # every cell, and once in each heading
     readme_100k = {10: (18.989, 5.76, 96.001), 20: (18.993, 10.65, 172.233), 50: (19.012, 25.22, 392.61)}
     for retx, (ratio, tx, delay) in readme_100k.items():
         table, ci = res[retx]
