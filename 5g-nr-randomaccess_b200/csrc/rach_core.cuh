@@ -35,6 +35,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include "rach_tape.h"
+#include "rach_warp.cuh"
 
 #ifdef __CUDACC__
 #define RA_HD __host__ __device__ __forceinline__
@@ -400,7 +401,7 @@ RA_HD void ra_job_init(const RaJobT<PT>& job, RaShared& s, int tid, int nt) {
  * view of the visible cohorts.
  * ========================================================================================= */
 template <class PT>
-RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt) {
+RA_HD void ra_phase0_classes(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt) {
     const PT& pt = *job.pt;
     const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1);
@@ -415,23 +416,34 @@ RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt)
         S_l1[p] = best; S_l1m[p] = bestm;
         S_l2[p] = RA_INF32; S_before[p] = 0; S_extraFirst[p] = 0; S_clsSize[p] = 0;
     }
-    if (tid == 0) {
-        if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) s.grantCheck = 0;          /* literal 5, W:268 */
-        s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
-        s.acOld = s.activeCheck;
-        if (T == s.nextArrMs) {                                                 /* T % accessTime == 0, W:280 */
-            if (s.activeCheck != pt.nUE) s.activeCheck = s.nextAc;
-            s.nextArrMs = T + pt.A; s.occ++;
-            if (s.occ < pt.nOcc) s.nextAc = pt.arrCum[s.occ];                   /* needed A ms from now: latency hidden */
-        }
-        s.nArr = s.activeCheck - s.acOld;
-        s.nMov = S_bcount[(unsigned)T & Rm];
-        /* every record of the bucket was granted before its window expired (the normal case under light load: the
-         * first scan of a lone UE is answered): nothing to read, nothing to move */
-        if (S_dead[(unsigned)T & Rm] == s.nMov) s.nMov = 0;
-        s.nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
-        s.recMoves += (ra_u64)s.nMov + s.nM3;
+}
+
+/* the control block of ms T (one thread) */
+template <class PT>
+RA_HD void ra_phase0_ctl(const RaJobT<PT>& job, RaShared& s, int T) {
+    const PT& pt = *job.pt;
+    const unsigned Rm = (unsigned)(pt.R - 1);
+    if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) s.grantCheck = 0;          /* literal 5, W:268 */
+    s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
+    s.acOld = s.activeCheck;
+    if (T == s.nextArrMs) {                                                 /* T % accessTime == 0, W:280 */
+        if (s.activeCheck != pt.nUE) s.activeCheck = s.nextAc;
+        s.nextArrMs = T + pt.A; s.occ++;
+        if (s.occ < pt.nOcc) s.nextAc = pt.arrCum[s.occ];                   /* needed A ms from now: latency hidden */
     }
+    s.nArr = s.activeCheck - s.acOld;
+    s.nMov = S_bcount[(unsigned)T & Rm];
+    /* every record of the bucket was granted before its window expired (the normal case under light load: the
+     * first scan of a lone UE is answered): nothing to read, nothing to move */
+    if (S_dead[(unsigned)T & Rm] == s.nMov) s.nMov = 0;
+    s.nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
+    s.recMoves += (ra_u64)s.nMov + s.nM3;
+}
+
+template <class PT>
+RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt) {
+    ra_phase0_classes(job, s, T, tid, nt);
+    if (tid == 0) ra_phase0_ctl(job, s, T);
 }
 
 /* =========================================================================================
@@ -840,6 +852,119 @@ RA_HD void ra_hist_clear(const PT& pt, const RaWork& w, RaShared& s, int tid, in
     const unsigned n = s.nSingles;
     if (n > RA_HBINS / 2) { for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0; }
     else for (unsigned j = tid; j < n; j += nt) S_hist[(j < RA_SCAP ? S_sIdx[j] : w.singles[j]) >> pt.hshift] = 0;
+}
+
+/* =========================================================================================
+ * A LIGHT ms, start to end, by ONE WARP without a block barrier (vector form of rach_warp.cuh).
+ *
+ * Most simulated ms have no mover at all: under Uniform traffic a lone UE is answered at its first scan and leaves
+ * only a dead record behind; under overload the movers sit in one ms of five.  What such a ms still does is small:
+ * a few arrivals and Msg3 answers (at most one per lane here), the re-scan of the visible classes -- every member is
+ * a non-mover, so a class of size n is one scan by its lowest index (W:613-662: n == 1 -> singleton, UL grant in index
+ * order while grantCheck < G, W:639-641; n > 1 -> collision counters) -- and the retirement of an empty bucket.
+ * The general path spends five block-wide barriers and seven passes on it; this routine fuses phases 0, 1, 4, 5 and 6
+ * into one warp-synchronous pass, and the kernel runs such ms back to back while the other warps wait at one barrier.
+ *
+ * returns 0  not a light ms (real movers, or more than 32 events): nothing was touched, run the general path
+ *         1  ms T is complete
+ *         2  the events (phase 1) are done but a Msg3 restart landed on this ms (W:693): continue with the general
+ *            path from the class view (ra_phase0_classes) and phase 2
+ *         3  complete except for a granted UE whose position hint was stale: run ra_phase6b
+ * ========================================================================================= */
+RW_FN unsigned rw_min_u32(const unsigned* a) {
+#ifdef __CUDA_ARCH__
+    unsigned v = a[0];
+    for (int o = 16; o > 0; o >>= 1) { const unsigned t = __shfl_xor_sync(0xFFFFFFFFu, v, o); v = t < v ? t : v; }
+    return v;
+#else
+    unsigned v = a[0];
+    for (int i = 1; i < 32; ++i) v = a[i] < v ? a[i] : v;
+    return v;
+#endif
+}
+
+template <bool DUMP, class PT>
+RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc* acc, int T) {
+    const PT& pt = *job.pt;
+    const int P = pt.P, Wn = pt.Wn;
+    const unsigned Rm = (unsigned)(pt.R - 1), slotT = (unsigned)T & Rm;
+    /* eligibility: pure reads */
+    if (S_bcount[slotT] != S_dead[slotT]) return 0;
+    int newAc = s.activeCheck;
+    if (T == s.nextArrMs && s.activeCheck != pt.nUE) newAc = s.nextAc;
+    const unsigned nEv = (unsigned)(newAc - s.activeCheck) + S_m3count[(unsigned)T & (RA_M3RING - 1)];
+    if (nEv > 32u) return 0;
+    RW_SYNC();                                              /* every lane has read the control block */
+    RW_EACH(l) if (lane == 0) ra_phase0_ctl(job, s, T);
+    RW_SYNC();
+    /* phase 1: arrivals, then Msg3 answers (s.nMov == 0), one per lane */
+    RW_EACH(l) if ((unsigned)lane < nEv) ra_phase1_item<DUMP>(job, w, s, acc[l], T, (unsigned)lane);
+    RW_SYNC();
+    if (s.nE1) return 2;
+    /* phases 0 + 4 fused: the class view, and the one scan per visible class (no mover, no re-transmitter, nobody left
+     * early: size = N, first scan by the lowest visible index) */
+    int f[RW_LANES];
+    unsigned nSing = 0;
+    for (int base = 0; base < P; base += 32) {
+        RW_EACH(l) {
+            const int q = base + lane;
+            f[l] = 0;
+            if (q < P) {
+                unsigned n = 0, best = RA_INF32, bestm = 0;
+                for (int d = 0; d < Wn; ++d) {
+                    const unsigned m = ((unsigned)(T + d) & Rm);
+                    n += S_cnt[m * P + q];
+                    if (d > 0) { const unsigned v = S_minI[m * P + q]; if (v < best) { best = v; bestm = m; } }
+                }
+                S_N[q] = n; S_l1[q] = best; S_l1m[q] = bestm;
+                if (n) ra_count_scan(acc[l], n);
+                f[l] = n == 1u;
+            }
+        }
+        nSing += (unsigned)RW_POPC(RW_BALLOT(f));
+    }
+    if (nSing) {
+        /* phase 5: the first G-1-grantCheck singleton scans in UE index order are granted (W:639-641) */
+        RW_SYNC();
+        long long K = (long long)pt.G - 1 - s.grantCheck;
+        if (K < 0) K = 0;
+        unsigned tau = RA_INF32, noGrant = 0;
+        if ((long long)nSing > K) {
+            if (K == 0) noGrant = 1;
+            else {
+                unsigned prev = 0; bool first = true;
+                for (long long r = 0; r < K; ++r) {
+                    unsigned bv[RW_LANES];
+                    RW_EACH(l) {
+                        bv[l] = RA_INF32;
+                        for (int q = lane; q < P; q += 32)
+                            if (S_N[q] == 1u) { const unsigned v = S_l1[q]; if ((first || v > prev) && v < bv[l]) bv[l] = v; }
+                    }
+                    prev = rw_min_u32(bv); first = false;
+                }
+                tau = prev;
+            }
+        }
+        /* phase 6: granted -> Msg3 calendar (W:642-645); the others stay where they are (txTime++ is implicit) */
+        if (!noGrant) {
+            RW_EACH(l) for (int q = lane; q < P; q += 32) {
+                if (S_N[q] != 1u || S_l1[q] > tau) continue;
+                const unsigned slot = S_l1m[q], hint = w.minPos[slot * P + q];
+                const size_t at = (size_t)slot * w.cap + hint;
+#ifndef RA_NO_POS_HINT
+                if (hint < S_bcount[slot] && w.bucket[at].x == S_l1[q]) ra_grant_nonmover<DUMP>(job, w, s, T, (unsigned)q, slot, at);
+                else
+#endif
+                { const unsigned k = RA_AADD(&s.nNl, 1u); S_nlList[k] = (unsigned)q; }      /* rare: found by ra_phase6b */
+            }
+        }
+        RW_SYNC();
+        RW_EACH(l) if (lane == 0) s.grantCheck += (int)nSing;
+    }
+    /* retire ms T: its bucket held dead records only, so its cohorts are already empty */
+    RW_EACH(l) if (lane == 0) { S_bcount[slotT] = 0; S_dead[slotT] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
+    RW_SYNC();
+    return s.nNl ? 3 : 1;
 }
 
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */

@@ -54,6 +54,9 @@
                               sector: 192 x 5 169 ms) */
 #endif
 #define RA_NPHASE 10
+#ifndef RA_LIGHT
+#define RA_LIGHT 1           /* 0: every ms takes the general (block-wide) path -- for cross-checks and A/B timing */
+#endif
 #ifndef RA_ILP
 #define RA_ILP 2             /* movers per thread and loop iteration (interleaved Philox chains) */
 #endif
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
     __shared__ RaShared s;
     __shared__ RaPointDev sPt;
     __shared__ int sJob;
+    __shared__ int sLight[4];                           /* warp 0 -> block: ms to resume at, how (ra_light_ms code), simTime */
     __shared__ ra_u64 sCyc[RA_NPHASE];
     long long tick = 0;
     const bool timers = a.phaseCycles != nullptr;     /* profiling aid (ra_options.phaseTimers), off by default */
@@ -113,10 +117,26 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
         int simTime = pt.maxTime;
         if (timers && tid == 0) tick = clock64();
         for (int T = 0;; ++T) {
-            ra_phase0(job, s, T, tid, nt);
+            /* warp 0 runs light ms (no movers, at most 32 events) back to back without any block barrier
+             * (ra_light_ms); at the first ms that needs the block it prepares that ms' class view and control block */
+            if (tid < 32) {
+                int code;
+                for (;;) {
+                    code = RA_LIGHT ? ra_light_ms<DUMP>(job, w, s, &acc, T) : 0;
+                    if (code != 1) break;
+                    if (ra_ms_done(pt, s, T, &simTime)) { code = 4; break; }
+                    ++T;
+                }
+                if (code == 0) ra_phase0(job, s, T, tid, 32);
+                else if (code == 2) ra_phase0_classes(job, s, T, tid, 32);
+                if (tid == 0) { sLight[0] = T; sLight[1] = code; sLight[2] = simTime; }
+            }
             __syncthreads();
+            T = sLight[0];
+            const int lightCode = sLight[1];
             RA_TICK(0);
-            {
+            if (lightCode == 4) { simTime = sLight[2]; break; }
+            if (lightCode == 0) {
                 /* movers: 128-bit coalesced loads of bucket T; two records per thread and iteration so that
                  * their two Philox chains interleave (the chain is 10 dependent rounds), next pair prefetched */
                 const unsigned nMov = s.nMov;
@@ -155,9 +175,10 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
 #endif
                 const unsigned n1 = nMov + (unsigned)s.nArr + s.nM3;
                 for (i = nMov + tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
+                __syncthreads();
+                RA_TICK(1);
             }
-            __syncthreads();
-            RA_TICK(1);
+            if (lightCode != 3) {
             if (s.nC3) {
                 if (tid == 0) ra_phase2_serial(pt, w, s);
                 __syncthreads();
@@ -193,6 +214,7 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             }
             __syncthreads();
             RA_TICK(7);
+            }
             if (s.nNl) {
                 ra_phase6b<DUMP>(job, w, s, T, tid, nt);
                 __syncthreads();

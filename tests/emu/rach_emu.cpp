@@ -20,7 +20,7 @@ extern "C" {
 #include "ref_api.h"
 }
 
-extern "C" { int emu_use_fixed = 1; }
+extern "C" { int emu_use_fixed = 1; int emu_light = 1; long long emu_light_ms = 0, emu_light_code2 = 0, emu_light_code3 = 0, emu_total_ms = 0; }
 
 template <bool DUMP, class PT>
 static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config* cfg, ref_result* res, int* perUE, int NT) {
@@ -29,10 +29,31 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
 
     for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
     int simTime = pt.maxTime;
+    RaAcc lacc[32]; memset(lacc, 0, sizeof lacc);              /* the 32 lanes of warp 0 in the light path */
+    bool done = false;
     for (int T = 0;; ++T) {
-        for (int t = 0; t < NT; ++t) ra_phase0(job, s, T, t, NT);
-        unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
+        /* the kernel's control flow: warp 0 runs light ms back to back (ra_light_ms, vector form: the 32 lanes are played
+         * by a loop), then prepares the first ms that needs the whole block */
+        int code;
+        for (;;) {
+            code = emu_light ? ra_light_ms<DUMP>(job, w, s, lacc, T) : 0;
+            if (code == 2) emu_light_code2++;
+            if (code == 3) emu_light_code3++;
+            if (code != 1) break;
+            emu_light_ms++; emu_total_ms++;
+            if (ra_ms_done(pt, s, T, &simTime)) { code = 4; break; }
+            ++T;
+        }
+        if (code == 4) { done = true; break; }
+        emu_total_ms++;
+        if (code == 0) {
+            for (int t = 0; t < 32; ++t) ra_phase0(job, s, T, t, 32);
+            unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
+            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
+        } else if (code == 2) {
+            for (int t = 0; t < 32; ++t) ra_phase0_classes(job, s, T, t, 32);
+        }
+        if (code != 3) {
         if (s.nC3) ra_phase2_serial(pt, w, s);
         if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
         if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
@@ -42,12 +63,18 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
         if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
+        }
         if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
         if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
         if (ra_ms_done(pt, s, T, &simTime)) break;
     }
+    (void)done;
     const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
     if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
+    for (int t = 0; t < 32; ++t) {
+        s.contFailed += lacc[t].contFailed; s.collP += lacc[t].collP; s.txop += lacc[t].txop;
+        s.collScans += lacc[t].collScans; s.totScans += lacc[t].totScans;
+    }
     for (int t = 0; t < NT; ++t) {
         s.contFailed += acc[t].contFailed; s.collP += acc[t].collP; s.txop += acc[t].txop;
         s.collScans += acc[t].collScans; s.totScans += acc[t].totScans;

@@ -158,3 +158,40 @@ def test_work_list_overflow_paths(oracle, tmp_path):
         for k in KEYS:
             assert getattr(p, k) == getattr(e, k), (k, kw)
         np.testing.assert_array_equal(ue, ue2, err_msg=str(kw))
+    # the light-ms path met both of its hand-overs to the general path: a Msg3 restart landing on the ms (code 2) and
+    # a granted UE that has to be searched for (code 3, forced by RA_NO_POS_HINT)
+    lib = C.CDLL(so)
+    assert C.c_longlong.in_dll(lib, "emu_light_code3").value > 0
+    assert C.c_longlong.in_dll(lib, "emu_light_ms").value > 0
+
+
+def test_light_ms_path_against_general_path(oracle, emu):
+    """ra_light_ms (one warp, no block barrier, phases 0/1/4/5/6 fused) must give what the general block-wide path gives:
+    same runs with the light path switched off, and the share of ms it takes is what makes it worth having."""
+    so = os.path.join(ROOT, "tests", "emu", "_build", "librach_emu.so")
+    lib = C.CDLL(so)
+    light, n_light, n_total, n_code2 = (C.c_int.in_dll(lib, "emu_light"), C.c_longlong.in_dll(lib, "emu_light_ms"),
+                                        C.c_longlong.in_dll(lib, "emu_total_ms"), C.c_longlong.in_dll(lib, "emu_light_code2"))
+    f, thr = emu
+    thr.value = 128
+    n_code2.value = 0
+    for kw, min_share in ((dict(nUE=100000, distribution=1, seed=3), 0.7), (dict(nUE=10000, seed=4), 0.6),
+                          (dict(nUE=40000, seed=5, stopMs=6000), 0.3), (dict(nUE=3000, nPreamble=3, nGrantUL=2, seed=5), 0.4),
+                          (dict(nUE=60000, distribution=1, nGrantUL=2, nPreamble=8, seed=6, stopMs=20000), 0.0)):
+        cfg = oracle.make_config(**kw)
+        out = []
+        for mode in (1, 0):
+            light.value = mode
+            n_light.value = 0
+            n_total.value = 0
+            e, ue, _ = oracle._run(f, cfg, True, False)
+            out.append((e, ue))
+            if mode:
+                assert n_light.value >= min_share * n_total.value, (kw, n_light.value, n_total.value)
+            else:
+                assert n_light.value == 0
+        light.value = 1
+        for k in KEYS:
+            assert getattr(out[0][0], k) == getattr(out[1][0], k), (k, kw)
+        np.testing.assert_array_equal(out[0][1], out[1][1], err_msg=str(kw))
+    assert n_code2.value > 0
