@@ -76,11 +76,20 @@ typedef unsigned long long ra_u64;
 #ifdef __CUDA_ARCH__
 #define RA_AADD(p, v)   atomicAdd((p), (v))
 #define RA_AMIN(p, v)   atomicMin((p), (v))
+/* 64-bit sum in shared memory fed with 32-bit addends: one native 32-bit atomic on the low word and a carry (a 64-bit
+ * shared-memory atomicAdd is a compare-and-swap loop) */
+__device__ __forceinline__ void ra_aadd64(unsigned long long* p, unsigned v) {
+    unsigned* w = reinterpret_cast<unsigned*>(p);
+    const unsigned old = atomicAdd(w, v);
+    if (old + v < old) atomicAdd(w + 1, 1u);
+}
+#define RA_AADD64(p, v) ra_aadd64((p), (v))
 #else
 template <class T> static inline T ra_emu_add(T* p, T v) { T o = *p; *p = o + v; return o; }
 template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
 #define RA_AADD(p, v)   ra_emu_add((p), (v))
 #define RA_AMIN(p, v)   ra_emu_min((p), (v))
+#define RA_AADD64(p, v) (*(p) += (unsigned long long)(v))
 #endif
 
 /* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1
@@ -510,6 +519,64 @@ RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s
     }
 }
 
+/* arrival of UE idx, W:383-394 + first draw W:477-487 */
+template <bool DUMP, class PT>
+RA_HD void ra_arrival_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, unsigned idx) {
+    const PT& pt = *job.pt;
+    rach_u32x4 d = ra_draws(job, idx, T);
+    unsigned p = pt.modP(d.v[pt.geometry ? 2 : 0] >> 1);
+    uint4 nr = make_uint4(idx, (unsigned)(T + 1), ra_z((unsigned)T, 0), ra_w3(p, 0, 1, 0));
+    if (DUMP) {
+        int* row = job.dump + (size_t)idx * RA_DUMP_W;
+        row[3] = T + 1; row[7] = 1;
+        row[15] = pt.geometry ? ra_sector((int)(d.v[0] >> 1)) : -1;
+    }
+    ra_schedule(pt, w, s, nr);
+}
+
+/* Msg3 / Msg4 of entry `item` of the Msg3 calendar of ms T, W:667-710; returns 1 if the UE finished */
+template <bool DUMP, class PT>
+RA_HD int ra_msg3_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
+    const PT& pt = *job.pt;
+    uint4 rec = w.msg3[(size_t)((unsigned)T & (RA_M3RING - 1)) * w.cap3 + item];
+    const unsigned idx = rec.x;
+    rach_u32x4 d = ra_draws(job, idx, T);
+    if (ra_rec_flag(rec) == 0) {                        /* connectionRequest 0 -> 1 < 48 */
+        if (rach_msg3_success((int)(d.v[0] >> 1))) {
+            unsigned timer = (unsigned)T - ra_rec_ts(rec) + 6;         /* W:674 */
+            RA_AADD(&s.nSuccess, 1u);
+            RA_AADD64(&s.txSum, ra_rec_ptc(rec));
+            RA_AADD64(&s.delaySum, timer);
+            RA_AADD64(&s.failSum, ra_rec_fail(rec));
+            if (DUMP) {
+                int* row = job.dump + (size_t)idx * RA_DUMP_W;
+                row[0] = (int)timer; row[1] = 0; row[2] = T; row[5] = 0;
+                row[6] = (int)ra_rec_p(rec); row[10] = (int)ra_rec_ptc(rec); row[11] = 1;
+                row[12] = 1; row[13] = 1; row[14] = (int)ra_rec_fail(rec);
+            }
+            return 1;
+        }
+        rec.y = (unsigned)(T + 48); rec.w |= 0x80000000u;   /* W:678-679 */
+        ra_msg3_push(pt, w, s, T + 48, rec);
+        return 0;
+    }
+    /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
+    acc.contFailed++;
+    int tmp = (int)pt.modBI(d.v[0] >> 1);
+    int X = ra_align(T + tmp, 5, RA_MAGIC5);
+    unsigned pnew = pt.modP(d.v[1] >> 1);
+    unsigned fail = ra_rec_fail(rec) + 1;
+    if (fail > 0xFFFFu) s.overflow = 2;
+    uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, ra_rec_ptc(rec), 0));
+    if (X == T) {                                       /* visible to later scanners, never scans */
+        unsigned e = RA_AADD(&s.nE1, 1u);
+        w.e1Rec[e] = nr; w.e1Meta[e] = 0;
+    } else {
+        ra_schedule(pt, w, s, nr);
+    }
+    return 0;
+}
+
 template <bool DUMP, class PT>
 RA_HD void ra_phase1_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item) {
     const PT& pt = *job.pt;
@@ -519,60 +586,9 @@ RA_HD void ra_phase1_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, R
         return;
     }
     item -= s.nMov;
-    if (item < (unsigned)s.nArr) {
-        /* ---------------- arrival, W:383-394 + first draw W:477-487 ---------------- */
-        unsigned idx = (unsigned)s.acOld + item;
-        rach_u32x4 d = ra_draws(job, idx, T);
-        unsigned p = pt.modP(d.v[pt.geometry ? 2 : 0] >> 1);
-        uint4 nr = make_uint4(idx, (unsigned)(T + 1), ra_z((unsigned)T, 0), ra_w3(p, 0, 1, 0));
-        if (DUMP) {
-            int* row = job.dump + (size_t)idx * RA_DUMP_W;
-            row[3] = T + 1; row[7] = 1;
-            row[15] = pt.geometry ? ra_sector((int)(d.v[0] >> 1)) : -1;
-        }
-        ra_schedule(pt, w, s, nr);
-        return;
-    }
+    if (item < (unsigned)s.nArr) { ra_arrival_item<DUMP>(job, w, s, T, (unsigned)s.acOld + item); return; }
     item -= (unsigned)s.nArr;
-    if (item < s.nM3) {
-        /* ---------------- Msg3 / Msg4, W:667-710 ---------------- */
-        uint4 rec = w.msg3[(size_t)((unsigned)T & (RA_M3RING - 1)) * w.cap3 + item];
-        const unsigned idx = rec.x;
-        rach_u32x4 d = ra_draws(job, idx, T);
-        if (ra_rec_flag(rec) == 0) {                        /* connectionRequest 0 -> 1 < 48 */
-            if (rach_msg3_success((int)(d.v[0] >> 1))) {
-                unsigned timer = (unsigned)T - ra_rec_ts(rec) + 6;         /* W:674 */
-                RA_AADD(&s.nSuccess, 1u);
-                RA_AADD(&s.txSum, (ra_u64)ra_rec_ptc(rec));
-                RA_AADD(&s.delaySum, (ra_u64)timer);
-                RA_AADD(&s.failSum, (ra_u64)ra_rec_fail(rec));
-                if (DUMP) {
-                    int* row = job.dump + (size_t)idx * RA_DUMP_W;
-                    row[0] = (int)timer; row[1] = 0; row[2] = T; row[5] = 0;
-                    row[6] = (int)ra_rec_p(rec); row[10] = (int)ra_rec_ptc(rec); row[11] = 1;
-                    row[12] = 1; row[13] = 1; row[14] = (int)ra_rec_fail(rec);
-                }
-            } else {                                        /* W:678-679 */
-                rec.y = (unsigned)(T + 48); rec.w |= 0x80000000u;
-                ra_msg3_push(pt, w, s, T + 48, rec);
-            }
-        } else {
-            /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
-            acc.contFailed++;
-            int tmp = (int)pt.modBI(d.v[0] >> 1);
-            int X = ra_align(T + tmp, 5, RA_MAGIC5);
-            unsigned pnew = pt.modP(d.v[1] >> 1);
-            unsigned fail = ra_rec_fail(rec) + 1;
-            if (fail > 0xFFFFu) s.overflow = 2;
-            uint4 nr = make_uint4(idx, (unsigned)X, ra_z((unsigned)T, fail), ra_w3(pnew, 0, ra_rec_ptc(rec), 0));
-            if (X == T) {                                   /* visible to later scanners, never scans */
-                unsigned e = RA_AADD(&s.nE1, 1u);
-                w.e1Rec[e] = nr; w.e1Meta[e] = 0;
-            } else {
-                ra_schedule(pt, w, s, nr);
-            }
-        }
-    }
+    if (item < s.nM3) ra_msg3_item<DUMP>(job, w, s, acc, T, item);
 }
 
 /* =========================================================================================
@@ -883,50 +899,88 @@ RW_FN unsigned rw_min_u32(const unsigned* a) {
 #endif
 }
 
+/* the control block of the replication as warp-uniform registers: warp 0 keeps it there while it runs light ms back to
+ * back (every lane computes the same updates) and writes it back to shared memory when the block takes over */
+struct RaCtl { int grantCheck, activeCheck, nextAc, nextArrMs, occ; unsigned nM3sum; };
+RA_HD RaCtl ra_ctl_load(const RaShared& s) {
+    RaCtl c; c.grantCheck = s.grantCheck; c.activeCheck = s.activeCheck; c.nextAc = s.nextAc; c.nextArrMs = s.nextArrMs;
+    c.occ = s.occ; c.nM3sum = 0;
+    return c;
+}
+RA_HD void ra_ctl_store(RaShared& s, const RaCtl& c) {           /* one thread */
+    s.grantCheck = c.grantCheck; s.activeCheck = c.activeCheck; s.nextAc = c.nextAc; s.nextArrMs = c.nextArrMs;
+    s.occ = c.occ; s.recMoves += c.nM3sum;
+}
+
+RA_HD void ra_lists_reset(RaShared& s) {                         /* one thread; what ra_phase0_ctl does per ms */
+    s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
+}
+
+/* done = 1 if the replication ended with this ms (everybody succeeded, or the horizon); on entry s.nE1 == s.nNl == 0 */
 template <bool DUMP, class PT>
-RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc* acc, int T) {
+RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl& c, RaAcc* acc, int T, int* done, int* simTime) {
     const PT& pt = *job.pt;
     const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1), slotT = (unsigned)T & Rm;
-    /* eligibility: pure reads */
+    /* eligibility: no state is touched before the ms is known to be light */
     if (S_bcount[slotT] != S_dead[slotT]) return 0;
-    int newAc = s.activeCheck;
-    if (T == s.nextArrMs && s.activeCheck != pt.nUE) newAc = s.nextAc;
-    const unsigned nEv = (unsigned)(newAc - s.activeCheck) + S_m3count[(unsigned)T & (RA_M3RING - 1)];
-    if (nEv > 32u) return 0;
-    RW_SYNC();                                              /* every lane has read the control block */
-    RW_EACH(l) if (lane == 0) ra_phase0_ctl(job, s, T);
+    const bool arrivalMs = T == c.nextArrMs;
+    const int newAc = (arrivalMs && c.activeCheck != pt.nUE) ? c.nextAc : c.activeCheck;
+    const unsigned nArr = (unsigned)(newAc - c.activeCheck), nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
+    if (nArr + nM3 > 32u) return 0;
+    /* control block of ms T (ra_phase0_ctl on registers) */
+    if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) c.grantCheck = 0;          /* literal 5, W:268 */
+    const unsigned acOld = (unsigned)c.activeCheck;
+    c.activeCheck = newAc;
+    if (arrivalMs) {
+        c.nextArrMs = T + pt.A; c.occ++;
+        if (c.occ < pt.nOcc) c.nextAc = pt.arrCum[c.occ];
+    }
+    c.nM3sum += nM3;
+    /* phase 1: arrivals (W:294-298), then Msg3 answers (W:318-321), one per lane */
+    int fin[RW_LANES];
+    RW_EACH(l) {
+        fin[l] = 0;
+        if ((unsigned)lane < nArr) ra_arrival_item<DUMP>(job, w, s, T, acOld + (unsigned)lane);
+        else if ((unsigned)lane < nArr + nM3) fin[l] = ra_msg3_item<DUMP>(job, w, s, acc[l], T, (unsigned)lane - nArr);
+    }
+    const unsigned anyFin = nM3 ? RW_BALLOT(fin) : 0u;
     RW_SYNC();
-    /* phase 1: arrivals, then Msg3 answers (s.nMov == 0), one per lane */
-    RW_EACH(l) if ((unsigned)lane < nEv) ra_phase1_item<DUMP>(job, w, s, acc[l], T, (unsigned)lane);
-    RW_SYNC();
-    if (s.nE1) return 2;
+    if (nM3 && s.nE1) return 2;
     /* phases 0 + 4 fused: the class view, and the one scan per visible class (no mover, no re-transmitter, nobody left
-     * early: size = N, first scan by the lowest visible index) */
-    int f[RW_LANES];
+     * early: size = N, first scan by the lowest visible index).  A cohort whose bucket holds no live record (empty, or
+     * every record granted away) has an all-zero row: skipped for all classes at once. */
+    const bool canSkip = Wn <= 32;                          /* one bit per cohort of the window */
+    unsigned liveSlots = canSkip ? 0u : 1u;
+    if (canSkip)
+        for (int d = 1; d < Wn; ++d) { const unsigned m = ((unsigned)(T + d) & Rm); if (S_bcount[m] != S_dead[m]) liveSlots |= 1u << d; }
     unsigned nSing = 0;
-    for (int base = 0; base < P; base += 32) {
-        RW_EACH(l) {
-            const int q = base + lane;
-            f[l] = 0;
-            if (q < P) {
-                unsigned n = 0, best = RA_INF32, bestm = 0;
-                for (int d = 0; d < Wn; ++d) {
-                    const unsigned m = ((unsigned)(T + d) & Rm);
-                    n += S_cnt[m * P + q];
-                    if (d > 0) { const unsigned v = S_minI[m * P + q]; if (v < best) { best = v; bestm = m; } }
+    if (liveSlots) {
+        int f[RW_LANES];
+        for (int base = 0; base < P; base += 32) {
+            RW_EACH(l) {
+                const int q = base + lane;
+                f[l] = 0;
+                if (q < P) {
+                    unsigned n = 0, best = RA_INF32, bestm = 0;
+                    for (int d = 1; d < Wn; ++d) {
+                        if (canSkip && !((liveSlots >> d) & 1u)) continue;
+                        const unsigned m = ((unsigned)(T + d) & Rm);
+                        n += S_cnt[m * P + q];
+                        const unsigned v = S_minI[m * P + q]; if (v < best) { best = v; bestm = m; }
+                    }
+                    S_N[q] = n; S_l1[q] = best; S_l1m[q] = bestm;
+                    if (n) ra_count_scan(acc[l], n);
+                    f[l] = n == 1u;
                 }
-                S_N[q] = n; S_l1[q] = best; S_l1m[q] = bestm;
-                if (n) ra_count_scan(acc[l], n);
-                f[l] = n == 1u;
             }
+            nSing += (unsigned)RW_POPC(RW_BALLOT(f));
         }
-        nSing += (unsigned)RW_POPC(RW_BALLOT(f));
     }
     if (nSing) {
         /* phase 5: the first G-1-grantCheck singleton scans in UE index order are granted (W:639-641) */
         RW_SYNC();
-        long long K = (long long)pt.G - 1 - s.grantCheck;
+        long long K = (long long)pt.G - 1 - c.grantCheck;
         if (K < 0) K = 0;
         unsigned tau = RA_INF32, noGrant = 0;
         if ((long long)nSing > K) {
@@ -958,13 +1012,19 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc
                 { const unsigned k = RA_AADD(&s.nNl, 1u); S_nlList[k] = (unsigned)q; }      /* rare: found by ra_phase6b */
             }
         }
-        RW_SYNC();
-        RW_EACH(l) if (lane == 0) s.grantCheck += (int)nSing;
+        c.grantCheck += (int)nSing;
     }
     /* retire ms T: its bucket held dead records only, so its cohorts are already empty */
-    RW_EACH(l) if (lane == 0) { S_bcount[slotT] = 0; S_dead[slotT] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
+    if (S_bcount[slotT] | nM3) {
+        RW_EACH(l) if (lane == 0) { S_bcount[slotT] = 0; S_dead[slotT] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
+    }
     RW_SYNC();
-    return s.nNl ? 3 : 1;
+    if (nSing && s.nNl) return 3;
+    /* W:330-334 and the loop bound W:267 */
+    *done = 0;
+    if (anyFin && s.nSuccess == (unsigned)pt.nUE) { *simTime = T; *done = 1; }
+    else if (T + 1 >= pt.maxTime) { *simTime = pt.maxTime; *done = 1; }
+    return 1;
 }
 
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */

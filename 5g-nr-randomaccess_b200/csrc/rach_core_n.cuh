@@ -377,8 +377,8 @@ RA_HD void rn_msg3_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T,
         if (rach_msg3_success((int)(d.v[0] >> 1))) {        /* N:504-508 */
             const unsigned timer = (unsigned)T - rn_ts(r) + 6;
             RA_AADD(&s.nSuccess, 1u);
-            RA_AADD(&s.txSum, (ra_u64)rn_ntx(r));
-            RA_AADD(&s.delaySum, (ra_u64)timer);
+            RA_AADD64(&s.txSum, rn_ntx(r));
+            RA_AADD64(&s.delaySum, timer);
             if (DUMP) {
                 int* row = job.dump + (size_t)idx * RA_DUMP_W;
                 row[0] = (int)timer; row[1] = 0; row[2] = T; row[5] = 0; row[6] = (int)rn_p(r); row[8] = 0;

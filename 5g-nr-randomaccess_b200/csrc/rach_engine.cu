@@ -120,12 +120,21 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             /* warp 0 runs light ms (no movers, at most 32 events) back to back without any block barrier
              * (ra_light_ms); at the first ms that needs the block it prepares that ms' class view and control block */
             if (tid < 32) {
-                int code;
-                for (;;) {
-                    code = RA_LIGHT ? ra_light_ms<DUMP>(job, w, s, &acc, T) : 0;
-                    if (code != 1) break;
-                    if (ra_ms_done(pt, s, T, &simTime)) { code = 4; break; }
-                    ++T;
+                int code = 0;
+                if (RA_LIGHT) {
+                    if (tid == 0) ra_lists_reset(s);
+                    __syncwarp();
+                    RaCtl c = ra_ctl_load(s);
+                    int done = 0;
+                    for (;;) {
+                        code = ra_light_ms<DUMP>(job, w, s, c, &acc, T, &done, &simTime);
+                        if (code != 1) break;
+                        if (done) { code = 4; break; }
+                        ++T;
+                    }
+                    __syncwarp();
+                    if (tid == 0) ra_ctl_store(s, c);
+                    __syncwarp();
                 }
                 if (code == 0) ra_phase0(job, s, T, tid, 32);
                 else if (code == 2) ra_phase0_classes(job, s, T, tid, 32);

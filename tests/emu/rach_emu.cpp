@@ -34,15 +34,21 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
     for (int T = 0;; ++T) {
         /* the kernel's control flow: warp 0 runs light ms back to back (ra_light_ms, vector form: the 32 lanes are played
          * by a loop), then prepares the first ms that needs the whole block */
-        int code;
-        for (;;) {
-            code = emu_light ? ra_light_ms<DUMP>(job, w, s, lacc, T) : 0;
-            if (code == 2) emu_light_code2++;
-            if (code == 3) emu_light_code3++;
-            if (code != 1) break;
-            emu_light_ms++; emu_total_ms++;
-            if (ra_ms_done(pt, s, T, &simTime)) { code = 4; break; }
-            ++T;
+        int code = 0;
+        if (emu_light) {
+            ra_lists_reset(s);
+            RaCtl c = ra_ctl_load(s);
+            int fin = 0;
+            for (;;) {
+                code = ra_light_ms<DUMP>(job, w, s, c, lacc, T, &fin, &simTime);
+                if (code == 2) emu_light_code2++;
+                if (code == 3) emu_light_code3++;
+                if (code != 1) break;
+                emu_light_ms++; emu_total_ms++;
+                if (fin) { code = 4; break; }
+                ++T;
+            }
+            ra_ctl_store(s, c);
         }
         if (code == 4) { done = true; break; }
         emu_total_ms++;

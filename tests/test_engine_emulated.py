@@ -177,7 +177,9 @@ def test_light_ms_path_against_general_path(oracle, emu):
     n_code2.value = 0
     for kw, min_share in ((dict(nUE=100000, distribution=1, seed=3), 0.7), (dict(nUE=10000, seed=4), 0.6),
                           (dict(nUE=40000, seed=5, stopMs=6000), 0.3), (dict(nUE=3000, nPreamble=3, nGrantUL=2, seed=5), 0.4),
-                          (dict(nUE=60000, distribution=1, nGrantUL=2, nPreamble=8, seed=6, stopMs=20000), 0.0)):
+                          (dict(nUE=60000, distribution=1, nGrantUL=2, nPreamble=8, seed=6, stopMs=20000), 0.0),
+                          (dict(nUE=2500, maxRarWindow=40, seed=7), 0.3),      # a window wider than the 32-bit slot mask
+                          (dict(nUE=20000, distribution=1, nPreamble=100, nGrantUL=3, seed=8, stopMs=15000), 0.3)):
         cfg = oracle.make_config(**kw)
         out = []
         for mode in (1, 0):
