@@ -717,6 +717,7 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
     }
     sim->stats.resize(nJobs);
     for (RaDev& d : sim->devs) {
+        if (d.jobs.empty()) continue;                     /* more devices than replications: nothing to set up there */
         int rc = ra_setup_device(sim, d);
         if (rc != RA_OK) { g_createErr = sim->err; g_createCode = rc; ra_sim_destroy(sim); return nullptr; }
     }

@@ -335,6 +335,23 @@ def test_noma_batch(pkg, oracle):
         assert int(st[0, rep]["nSuccess"]) == res.nSuccess and int(st[0, rep]["delaySum"]) == res.delaySum
 
 
+def test_device_list_longer_than_the_job_list(pkg, oracle):
+    """ra_sim_create(devices[]) with more device entries than replications (entries may repeat a device id: each entry is
+    a shard with its own stream and workspace): the idle entries are skipped, the others give the usual results -- also
+    through the streaming run."""
+    p = pkg.default_params(nUE=4000, seed=8)
+    got = {}
+    with pkg.RachSim([p], reps=2, devices=[0, 0, 0, 0], rep_offset=3, dump_ues=True) as sim:
+        sim.run_stream(lambda point, rep, st, rows: got.__setitem__(rep, rows))
+        st = sim.stats_all()
+        for rep in (0, 1):
+            res, ue_ref, _ = oracle.run_port(oracle.make_config(nUE=4000, seed=8, rep=3 + rep))
+            for k in KEYS:
+                assert int(st[0, rep][k]) == getattr(res, k), (rep, k)
+            np.testing.assert_array_equal(got[rep], ue_ref)
+            np.testing.assert_array_equal(sim.dump_ues(0, rep), ue_ref)
+
+
 def test_multi_device_in_one_process(pkg):
     """ra_sim_create(devices[]) shards one job list over several GPUs from a single host thread;
     results equal the single-device run (skipped on a 1-GPU box)."""
