@@ -1027,15 +1027,6 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
     return 1;
 }
 
-/* may ms T run as a SMALL ms (every general phase by one warp)?  pure reads */
-template <class PT>
-RA_HD bool ra_small_ms_ok(const PT& pt, const RaShared& s, const RaCtl& c, int T) {
-    (void)s;
-    const int newAc = (T == c.nextArrMs && c.activeCheck != pt.nUE) ? c.nextAc : c.activeCheck;
-    return S_bcount[(unsigned)T & (unsigned)(pt.R - 1)] <= 32u &&
-           (unsigned)(newAc - c.activeCheck) + S_m3count[(unsigned)T & (RA_M3RING - 1)] <= 32u;
-}
-
 /* after phase 6 (every thread, same answer): W:330-334 and the loop bound W:267 */
 template <class PT>
 RA_HD bool ra_ms_done(const PT& pt, const RaShared& s, int T, int* simTime) {

@@ -81,27 +81,6 @@ struct RaKernelArgs {
     int               nJobs, maxP, maxR;
 };
 
-/* One SMALL ms -- at most 32 records in bucket T and at most 32 arrivals + Msg3 answers -- by one warp: the general
- * phases of rach_core.cuh with 32 "threads" and warp barriers instead of block barriers. */
-template <bool DUMP, class PT>
-__device__ __forceinline__ void ra_small_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, int lane) {
-    const PT& pt = *job.pt;
-    ra_phase0(job, s, T, lane, 32);
-    __syncwarp();
-    { const unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3; for (unsigned i = lane; i < n1; i += 32) ra_phase1_item<DUMP>(job, w, s, acc, T, i); }
-    __syncwarp();
-    if (s.nC3) { if (lane == 0) ra_phase2_serial(pt, w, s); __syncwarp(); }
-    if (s.nUnc) { const unsigned n = s.nUnc; for (unsigned i = lane; i < n; i += 32) ra_phase3_item<DUMP>(job, w, s, T, i); __syncwarp(); }
-    if (s.nE1) { const unsigned n = s.nE1; for (unsigned i = lane; i < n; i += 32) ra_phase3b_item(pt, w, s, i); __syncwarp(); }
-    { const unsigned n4 = (unsigned)pt.P + s.nLanders; for (unsigned i = lane; i < n4; i += 32) ra_phase4_item(pt, w, s, acc, i); }
-    __syncwarp();
-    if (s.nSingles) { ra_phase5_warp(pt, w, s, lane); __syncwarp(); }
-    { const unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1; for (unsigned i = lane; i < n6; i += 32) ra_phase6_item<DUMP>(job, w, s, T, i); }
-    if (s.nSingles) ra_hist_clear(pt, w, s, lane, 32);
-    __syncwarp();
-    if (s.nNl) { ra_phase6b<DUMP>(job, w, s, T, lane, 32); __syncwarp(); }
-}
-
 template <bool DUMP, int NT, int MINB, bool FIXED>
 __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
     /* FIXED: every point of the launch belongs to the reference's default family (54 preambles, BI 20, subframe 5, RAR
@@ -149,19 +128,9 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                     int done = 0;
                     for (;;) {
                         code = ra_light_ms<DUMP>(job, w, s, c, &acc, T, &done, &simTime);
-                        if (code == 1) { if (done) { code = 4; break; } ++T; continue; }
-                        /* not light, but SMALL (at most 32 records in the bucket and at most 32 other events): the general
-                         * phases, run by this warp alone with warp barriers -- a lightly loaded replication never needs the block */
-                        if (code != 0 || !ra_small_ms_ok(pt, s, c, T)) break;
-                        __syncwarp();
-                        if (tid == 0) ra_ctl_store(s, c);
-                        __syncwarp();
-                        ra_small_ms<DUMP>(job, w, s, acc, T, tid);
-                        if (ra_ms_done(pt, s, T, &simTime)) { code = 4; break; }
+                        if (code != 1) break;
+                        if (done) { code = 4; break; }
                         ++T;
-                        if (tid == 0) ra_lists_reset(s);
-                        __syncwarp();
-                        c = ra_ctl_load(s);
                     }
                     __syncwarp();
                     if (tid == 0) ra_ctl_store(s, c);
@@ -333,8 +302,10 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
         __syncthreads();
         int simTime = pt.maxTime;
         const unsigned Rm = (unsigned)(pt.R - 1);
+        int nextOcc = 0;                                               /* next ms with T % accessTime == 0 (no division per ms) */
         for (int T = 0; T < pt.maxTime; ++T) {
-            if (T % pt.A == 0) {                                        /* a RACH occasion, N:668 */
+            if (T == nextOcc) {                                         /* a RACH occasion, N:668 */
+                nextOcc += pt.A;
                 rn_phaseA0(job, s, T, tid, nt);
                 __syncthreads();
                 for (unsigned i = tid; i < (unsigned)s.nArr; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i);

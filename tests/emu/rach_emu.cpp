@@ -20,7 +20,7 @@ extern "C" {
 #include "ref_api.h"
 }
 
-extern "C" { int emu_use_fixed = 1; int emu_light = 1; long long emu_light_ms = 0, emu_light_code2 = 0, emu_light_code3 = 0, emu_total_ms = 0, emu_small_ms = 0; }
+extern "C" { int emu_use_fixed = 1; int emu_light = 1; long long emu_light_ms = 0, emu_light_code2 = 0, emu_light_code3 = 0, emu_total_ms = 0; }
 
 template <bool DUMP, class PT>
 static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config* cfg, ref_result* res, int* perUE, int NT) {
@@ -29,14 +29,12 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
 
     for (int t = 0; t < NT; ++t) ra_job_init<DUMP>(job, s, t, NT);
     int simTime = pt.maxTime;
-    RaAcc lacc[32]; memset(lacc, 0, sizeof lacc);
-    std::vector<RaAcc> sacc(32); memset(sacc.data(), 0, sizeof(RaAcc) * 32);   /* warp 0 in small ms */              /* the 32 lanes of warp 0 in the light path */
+    RaAcc lacc[32]; memset(lacc, 0, sizeof lacc);              /* the 32 lanes of warp 0 in the light path */
     bool done = false;
     for (int T = 0;; ++T) {
         /* the kernel's control flow: warp 0 runs light ms back to back (ra_light_ms, vector form: the 32 lanes are played
          * by a loop), then prepares the first ms that needs the whole block */
         int code = 0;
-        bool small = false;
         if (emu_light) {
             ra_lists_reset(s);
             RaCtl c = ra_ctl_load(s);
@@ -50,44 +48,35 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
                 if (fin) { code = 4; break; }
                 ++T;
             }
-            /* a small ms: the general phases below with 32 threads (the kernel runs them in warp 0 with warp barriers) */
-            small = code == 0 && ra_small_ms_ok(pt, s, c, T);
             ra_ctl_store(s, c);
-            if (small) emu_small_ms++;
         }
-        const int NTe = small ? 32 : NT;
-        std::vector<RaAcc>& accv = small ? sacc : acc;
         if (code == 4) { done = true; break; }
         emu_total_ms++;
         if (code == 0) {
             for (int t = 0; t < 32; ++t) ra_phase0(job, s, T, t, 32);
             unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-            for (int t = 0; t < NTe; ++t) for (unsigned i = t; i < n1; i += NTe) ra_phase1_item<DUMP>(job, w, s, accv[t], T, i);
+            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
         } else if (code == 2) {
             for (int t = 0; t < 32; ++t) ra_phase0_classes(job, s, T, t, 32);
         }
         if (code != 3) {
         if (s.nC3) ra_phase2_serial(pt, w, s);
-        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NTe; ++t) for (unsigned i = t; i < n; i += NTe) ra_phase3_item<DUMP>(job, w, s, T, i); }
-        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NTe; ++t) for (unsigned i = t; i < n; i += NTe) ra_phase3b_item(pt, w, s, i); }
+        if (s.nUnc) { unsigned n = s.nUnc; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3_item<DUMP>(job, w, s, T, i); }
+        if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
         unsigned n4 = (unsigned)pt.P + s.nLanders;
-        for (int t = 0; t < NTe; ++t) for (unsigned i = t; i < n4; i += NTe) ra_phase4_item(pt, w, s, accv[t], i);
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
         if (s.nSingles) ra_phase5_serial(pt, w, s);
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
-        for (int t = 0; t < NTe; ++t) for (unsigned i = t; i < n6; i += NTe) ra_phase6_item<DUMP>(job, w, s, T, i);
-        if (s.nSingles) for (int t = 0; t < NTe; ++t) ra_hist_clear(pt, w, s, t, NTe);
+        for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
+        if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
         }
-        if (s.nNl) for (int t = 0; t < NTe; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NTe);
+        if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
         if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
         if (ra_ms_done(pt, s, T, &simTime)) break;
     }
     (void)done;
     const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
     if (DUMP) for (int t = 0; t < NT; ++t) ra_dump_inflight(job, w, s, last, t, NT);
-    for (int t = 0; t < 32; ++t) {
-        s.contFailed += sacc[t].contFailed; s.collP += sacc[t].collP; s.txop += sacc[t].txop;
-        s.collScans += sacc[t].collScans; s.totScans += sacc[t].totScans;
-    }
     for (int t = 0; t < 32; ++t) {
         s.contFailed += lacc[t].contFailed; s.collP += lacc[t].collP; s.txop += lacc[t].txop;
         s.collScans += lacc[t].collScans; s.totScans += lacc[t].totScans;

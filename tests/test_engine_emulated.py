@@ -197,14 +197,3 @@ def test_light_ms_path_against_general_path(oracle, emu):
             assert getattr(out[0][0], k) == getattr(out[1][0], k), (k, kw)
         np.testing.assert_array_equal(out[0][1], out[1][1], err_msg=str(kw))
     assert n_code2.value > 0
-    # ms that are not light but small (at most 32 records / 32 events) run every general phase with the 32 threads of
-    # warp 0: under Uniform traffic that is every remaining ms
-    n_small = C.c_longlong.in_dll(lib, "emu_small_ms")
-    n_small.value = 0
-    n_light.value = 0
-    n_total.value = 0
-    cfg = oracle.make_config(nUE=100000, distribution=1, seed=9, stopMs=12000)
-    e, ue, _ = oracle._run(f, cfg, True, False)
-    p, ue_ref, _ = oracle.run_port(cfg)
-    np.testing.assert_array_equal(ue, ue_ref)
-    assert n_small.value > 1000 and n_small.value + n_light.value >= n_total.value - 2

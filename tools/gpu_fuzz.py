@@ -16,6 +16,13 @@ while time.time() - t0 < budget:
               nGrantUL=rnd.choice([2, 4, 8, 12, 12, 16, 54]), maxRarWindow=rnd.choice([3, 6, 6, 6, 11]),
               maxMsg2TxCount=rnd.choice([2, 9, 9, 19, 49]), accessTime=rnd.choice([5, 5, 5, 6, 8, 10]),
               seed=rnd.getrandbits(64), geometry=rnd.choice([0, 1]))
+    if rnd.random() < 0.5:                       # the reference's default family: the compile-time point view
+        kw.update(nPreamble=54, backoffIndicator=20, maxRarWindow=6, accessTime=5)
+    shape, fixed = rnd.choice(["", "", "small", "big", "huge"]), rnd.choice(["1", "1", "0"])
+    os.environ.pop("RACH_BLOCK", None)
+    if shape:
+        os.environ["RACH_BLOCK"] = shape
+    os.environ["RACH_FIXED"] = fixed
     rep = rnd.randrange(100000)
     res, ue_ref, _ = O.run_port(O.make_config(rep=rep, **kw))
     with pkg.RachSim([pkg.default_params(**kw)], reps=1, devices=[0], rep_offset=rep, dump_ues=True) as sim:
@@ -26,5 +33,5 @@ while time.time() - t0 < budget:
     n += 1
     if diff or nd:
         bad += 1
-        print("MISMATCH", kw, rep, diff, nd, flush=True)
+        print("MISMATCH", kw, rep, shape, fixed, diff, nd, flush=True)
 print("gpu fuzz: %d cases, %d bad, %.0f s" % (n, bad, time.time() - t0))
