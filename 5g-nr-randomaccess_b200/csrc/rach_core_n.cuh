@@ -147,10 +147,9 @@ RA_HD void rn_phaseA0(const RaJob& job, RaSharedN& s, int T, int tid, int nt) {
 /* ---- occasion phase A1: activeUE N:131-192 for the new arrivals; they transmit in this occasion ---- */
 template <bool DUMP>
 #define RN_MAX_REJECT 65536   /* draws one rejection loop of activeUE may take before the engine gives up (RA_E_INTERNAL) */
-RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, unsigned item) {
+RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T, unsigned idx) {
     const RaPointDev& pt = *job.pt;
     const float cellRadius = pt.cellRadius;
-    const unsigned idx = (unsigned)s.acOld + item;
     RaStream st = ra_stream(job, idx, T);
     const float pi = 3.14;
     const unsigned p = ra_mod((unsigned)ra_stream_next(st), (unsigned)pt.P, pt.magicP);            /* N:133 */

@@ -42,8 +42,10 @@
 #ifndef RA_MINB
 #define RA_MINB 9
 #endif
+#ifndef RA_NT_BIG
 #define RA_NT_BIG 256
 #define RA_MINB_BIG 5
+#endif
 /* few replications per device (strong scaling, small sweeps): one replication cannot be split over blocks, so the block
  * grows instead -- 512 threads x 2 per SM (64 registers) when there are at most two replications per SM */
 #define RA_NT_HUGE 512
@@ -302,13 +304,16 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
         __syncthreads();
         int simTime = pt.maxTime;
         const unsigned Rm = (unsigned)(pt.R - 1);
-        int nextOcc = 0;                                               /* next ms with T % accessTime == 0 (no division per ms) */
+        int nextOcc = 0, occ = 0;                                      /* next ms with T % accessTime == 0 (no division per ms) */
         for (int T = 0; T < pt.maxTime; ++T) {
             if (T == nextOcc) {                                         /* a RACH occasion, N:668 */
                 nextOcc += pt.A;
+                /* the arrival gate (N:675-681) is read by every thread from the schedule, so the table clearing / control
+                 * block (A0) and the arrivals (A1: calendar appends only) share one phase */
+                const unsigned acOld = occ ? (unsigned)pt.arrCum[occ - 1] : 0u, acNew = (unsigned)pt.arrCum[occ];
+                ++occ;
                 rn_phaseA0(job, s, T, tid, nt);
-                __syncthreads();
-                for (unsigned i = tid; i < (unsigned)s.nArr; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i);
+                for (unsigned i = acOld + tid; i < acNew; i += nt) rn_phaseA1_item<DUMP>(job, w, s, T, i);
                 __syncthreads();
                 const unsigned nTx = s.bcount[(unsigned)T & Rm];
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseA2_item(pt, w, s, T, j);
@@ -317,14 +322,14 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
                 __syncthreads();
                 for (unsigned j = tid; j < nTx; j += nt) rn_phaseC_item<DUMP>(job, w, s, T, j);
                 __syncthreads();
-                if (tid == 0) s.bcount[(unsigned)T & Rm] = 0;
+                if (tid == 0) s.bcount[(unsigned)T & Rm] = 0;           /* the slot is next used a ring later */
             }
             const unsigned nM3 = s.m3count[(unsigned)T & (RA_M3RING - 1)];
             if (nM3) {                                                  /* N:699 */
                 for (unsigned j = tid; j < nM3; j += nt) rn_msg3_item<DUMP>(job, w, s, T, j);
                 __syncthreads();
+                /* every thread has read this slot's count above and nobody reads it again before T + 64 */
                 if (tid == 0) s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
-                __syncthreads();
                 if (s.nSuccess == (unsigned)pt.nUE) { simTime = T; break; }   /* N:707-710 */
             }
         }

@@ -196,7 +196,7 @@ static int emu_run_n_t(const ref_config* cfg, ref_result* res, int* perUE, doubl
     for (int T = 0; T < pt.maxTime; ++T) {
         if (T % pt.A == 0) {
             for (int t = 0; t < NT; ++t) rn_phaseA0(job, s, T, t, NT);
-            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, i);
+            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < (unsigned)s.nArr; i += NT) rn_phaseA1_item<DUMP>(job, w, s, T, (unsigned)s.acOld + i);
             const unsigned nTx = s.bcount[(unsigned)T & Rm];
             for (int t = 0; t < NT; ++t) for (unsigned j = t; j < nTx; j += NT) rn_phaseA2_item(pt, w, s, T, j);
             for (int sec = 0; sec < (pt.geometry ? RA_NSECT : 1); ++sec) {       /* warp form (the kernel's) or the one-thread statement */
