@@ -200,7 +200,8 @@ struct RaShared {
     int grantCheck, activeCheck, acOld, nArr, overflow, nextAc;   /* nextAc: activeCheck after the next arrival step */
     int nextArrMs, occ;       /* next ms with T % A == 0 and its occasion number (no division in the ms loop) */
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
-    unsigned nSuccess, noGrant, nNl, pad1;
+    unsigned nSuccess, noGrant, nNl, nNlLight;      /* nNlLight: stale position hints met by ra_light_ms (its own counter:
+                                                      the block may still be reading nNl of the ms it has just finished) */
     ra_u64 txSum, delaySum, failSum, contFailed, collP, txop, collScans, totScans;
     ra_u64 recMoves;          /* records read from the calendars (move buckets, Msg3 ring, same-ms work list)     */
 };
@@ -849,9 +850,9 @@ RA_HD void ra_phase6_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, i
  * was stale (two UEs lowered the cohort minimum at the same time): find the record in the bucket of its move
  * time by index. */
 template <bool DUMP, class PT>
-RA_HD void ra_phase6b(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, int tid, int nt) {
+RA_HD void ra_phase6b(const RaJobT<PT>& job, const RaWork& w, RaShared& s, int T, int tid, int nt, unsigned nNl) {
     const PT& pt = *job.pt;
-    for (unsigned e = 0; e < s.nNl; ++e) {
+    for (unsigned e = 0; e < nNl; ++e) {
         const unsigned q = S_nlList[e], slot = S_l1m[q], want = S_l1[q];
         const unsigned n = S_bcount[slot];
         for (unsigned j = tid; j < n; j += nt) {
@@ -914,9 +915,10 @@ RA_HD void ra_ctl_store(RaShared& s, const RaCtl& c) {           /* one thread *
 
 RA_HD void ra_lists_reset(RaShared& s) {                         /* one thread; what ra_phase0_ctl does per ms */
     s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
+    s.nNlLight = 0;
 }
 
-/* done = 1 if the replication ended with this ms (everybody succeeded, or the horizon); on entry s.nE1 == s.nNl == 0 */
+/* done = 1 if the replication ended with this ms (everybody succeeded, or the horizon); on entry s.nE1 == s.nNlLight == 0 */
 template <bool DUMP, class PT>
 RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl& c, RaAcc* acc, int T, int* done, int* simTime) {
     const PT& pt = *job.pt;
@@ -1009,7 +1011,7 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
                 if (hint < S_bcount[slot] && w.bucket[at].x == S_l1[q]) ra_grant_nonmover<DUMP>(job, w, s, T, (unsigned)q, slot, at);
                 else
 #endif
-                { const unsigned k = RA_AADD(&s.nNl, 1u); S_nlList[k] = (unsigned)q; }      /* rare: found by ra_phase6b */
+                { const unsigned k = RA_AADD(&s.nNlLight, 1u); S_nlList[k] = (unsigned)q; }      /* rare: found by ra_phase6b */
             }
         }
         c.grantCheck += (int)nSing;
@@ -1019,7 +1021,7 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
         RW_EACH(l) if (lane == 0) { S_bcount[slotT] = 0; S_dead[slotT] = 0; S_m3count[(unsigned)T & (RA_M3RING - 1)] = 0; }
     }
     RW_SYNC();
-    if (nSing && s.nNl) return 3;
+    if (nSing && s.nNlLight) return 3;
     /* W:330-334 and the loop bound W:267 */
     *done = 0;
     if (anyFin && s.nSuccess == (unsigned)pt.nUE) { *simTime = T; *done = 1; }

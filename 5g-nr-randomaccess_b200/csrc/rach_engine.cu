@@ -118,29 +118,36 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
 
         int simTime = pt.maxTime;
         if (timers && tid == 0) tick = clock64();
-        for (int T = 0;; ++T) {
-            /* warp 0 runs light ms (no movers, at most 32 events) back to back without any block barrier
-             * (ra_light_ms); at the first ms that needs the block it prepares that ms' class view and control block */
+        /* The loop over the ms.  Warp 0 owns the control flow: it decides whether the replication has ended (W:330-334 and
+         * the loop bound W:267; no other warp reads nSuccess, which warp 0 may already be changing in a later light ms),
+         * runs light ms (no movers, at most 32 events) back to back without any block barrier (ra_light_ms), and at the
+         * first ms that needs the block prepares that ms' class view and control block.  It publishes (ms to run, how,
+         * simTime) through sLight. */
+        for (int T = 0, first = 1;; first = 0) {
             if (tid < 32) {
                 int code = 0;
-                if (RA_LIGHT) {
-                    if (tid == 0) ra_lists_reset(s);
-                    __syncwarp();
-                    RaCtl c = ra_ctl_load(s);
-                    int done = 0;
-                    for (;;) {
-                        code = ra_light_ms<DUMP>(job, w, s, c, &acc, T, &done, &simTime);
-                        if (code != 1) break;
-                        if (done) { code = 4; break; }
-                        ++T;
+                if (!first && ra_ms_done(pt, s, T, &simTime)) code = 4;           /* the ms the block has just finished */
+                else {
+                    if (!first) ++T;
+                    if (RA_LIGHT) {
+                        if (tid == 0) ra_lists_reset(s);
+                        __syncwarp();
+                        RaCtl c = ra_ctl_load(s);
+                        int done = 0;
+                        for (;;) {
+                            code = ra_light_ms<DUMP>(job, w, s, c, &acc, T, &done, &simTime);
+                            if (code != 1) break;
+                            if (done) { code = 4; break; }
+                            ++T;
+                        }
+                        __syncwarp();
+                        if (tid == 0) ra_ctl_store(s, c);
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    if (tid == 0) ra_ctl_store(s, c);
-                    __syncwarp();
+                    if (code == 0) ra_phase0(job, s, T, tid, 32);
+                    else if (code == 2) ra_phase0_classes(job, s, T, tid, 32);
                 }
-                if (code == 0) ra_phase0(job, s, T, tid, 32);
-                else if (code == 2) ra_phase0_classes(job, s, T, tid, 32);
-                if (tid == 0) { sLight[0] = T; sLight[1] = code; sLight[2] = simTime; }
+                if (tid == 0) { sLight[0] = T; sLight[1] = code; sLight[2] = simTime; sLight[3] = (int)s.nNlLight; }
             }
             __syncthreads();
             T = sLight[0];
@@ -226,12 +233,15 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             __syncthreads();
             RA_TICK(7);
             }
-            if (s.nNl) {
-                ra_phase6b<DUMP>(job, w, s, T, tid, nt);
-                __syncthreads();
-                RA_TICK(8);
+            {
+                /* stale position hints: of this ms' general phase 6, or handed over by ra_light_ms (code 3, count in sLight) */
+                const unsigned nNl = lightCode == 3 ? (unsigned)sLight[3] : s.nNl;
+                if (nNl) {
+                    ra_phase6b<DUMP>(job, w, s, T, tid, nt, nNl);
+                    __syncthreads();
+                    RA_TICK(8);
+                }
             }
-            if (ra_ms_done(pt, s, T, &simTime)) break;
         }
         const int last = simTime < pt.maxTime ? simTime : pt.maxTime - 1;
         if (DUMP) ra_dump_inflight(job, w, s, last, tid, nt);
@@ -328,9 +338,12 @@ __global__ void __launch_bounds__(RA_NT_N, RA_MINB_N) ra_step_kernel_n(RaKernelA
             if (nM3) {                                                  /* N:699 */
                 for (unsigned j = tid; j < nM3; j += nt) rn_msg3_item<DUMP>(job, w, s, T, j);
                 __syncthreads();
-                /* every thread has read this slot's count above and nobody reads it again before T + 64 */
                 if (tid == 0) s.m3count[(unsigned)T & (RA_M3RING - 1)] = 0;
-                if (s.nSuccess == (unsigned)pt.nUE) { simTime = T; break; }   /* N:707-710 */
+                const bool allDone = s.nSuccess == (unsigned)pt.nUE;          /* N:707-710 */
+                /* nobody may start the Msg3 answers of a later ms (they change nSuccess) before every thread has taken
+                 * this decision */
+                __syncthreads();
+                if (allDone) { simTime = T; break; }
             }
         }
         __syncthreads();

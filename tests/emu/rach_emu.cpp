@@ -70,7 +70,8 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
         if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
         }
-        if (s.nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT);
+        { const unsigned nNl = code == 3 ? s.nNlLight : s.nNl;
+          if (nNl) for (int t = 0; t < NT; ++t) ra_phase6b<DUMP>(job, w, s, T, t, NT, nNl); }
         if (s.overflow) { fprintf(stderr, "emu: overflow flag %d at ms %d\n", s.overflow, T); return -3; }
         if (ra_ms_done(pt, s, T, &simTime)) break;
     }
