@@ -5,9 +5,10 @@
  * One thread block simulates one replication from ms 0 to the horizon: it owns the move /
  * Msg3 calendars of that replication in HBM (16-byte records, 128-bit loads and stores) and
  * the per-preamble cohort tables in shared memory, and runs the phases of rach_core.cuh with
- * __syncthreads() in between.  Blocks are persistent: grid = min(jobs, SMs * CTAs/SM) and
- * each block pulls replications from an atomic job counter.  Replications never exchange
- * data, so multi-GPU is a partition of the job list (no collective in the data path).
+ * __syncthreads() in between -- except the ms without movers, which warp 0 runs alone, back to
+ * back, without a block barrier (ra_light_ms).  Blocks are persistent: grid = min(jobs, SMs *
+ * CTAs/SM) and each block pulls replications from an atomic job counter.  Replications never
+ * exchange data, so multi-GPU is a partition of the job list (no collective in the data path).
  *
  * Replaces the body of the reference's (seed, nUE) loop, RandomAccessWithNOMA.c:229-368.
  * There is no CPU path in this library.

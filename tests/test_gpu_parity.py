@@ -168,6 +168,33 @@ def test_full_size_100k_beta(pkg, oracle):
     assert st.simTimeMs == 10000 and 18000 < st.nSuccess < 20000     # README.md:97: 18.99 %
 
 
+def test_the_bench_batch_itself(pkg, golden):
+    """The headline workload as bench.py launches it (100k UEs x 4096 replications, seed 0, replication ids 0..4095), checked
+    through what does not need a CPU run per replication: replication 0 IS the reference's own 100 000-UE run (fixture
+    w_default_100000, generated by RandomAccessWithNOMA.c itself in tape mode); a second launch gives the same 4096 x 12
+    counters bit for bit (no result depends on the order of atomics or on which block ran what); a 40-replication launch
+    reproduces its slice; nobody finishes early, so the update count is exactly nUE x 2000 per replication; and the batch
+    means sit on the README row (README.md:97)."""
+    stats, _ = golden
+    g = stats["w_default_100000"]
+    p = pkg.default_params(nUE=100000, seed=0)
+    with pkg.RachSim([p], reps=4096, devices=[0]) as sim:
+        sim.run()
+        a = sim.stats_all().copy()
+        sim.run()
+        b = sim.stats_all().copy()
+    assert (a == b).all()
+    for k in KEYS[:8]:
+        assert int(a[0, 0][k]) == g["stats"][k], k
+    with pkg.RachSim([p], reps=40, devices=[0], rep_offset=1000) as sim:
+        sim.run()
+        assert (sim.stats_all()[0] == a[0, 1000:1040]).all()
+    assert (a["simTimeMs"] == 10000).all() and (a["updates"] == 100000 * 2000).all()
+    ns = a["nSuccess"].astype(np.float64)
+    assert abs(100.0 * ns.mean() / 100000 - 18.989) < 0.05
+    assert abs(a["preambleTxSum"].sum() / ns.sum() - 5.76) < 0.02 and abs(a["delaySum"].sum() / ns.sum() - 96.001) < 0.3
+
+
 def test_full_size_100k_uniform(pkg, oracle):
     """BASELINE configs[1]: Uniform 60 s, 100k UEs."""
     kw = dict(nUE=100000, distribution=1, seed=3, rep=1)
