@@ -764,7 +764,7 @@ static int ra_launch_device(ra_sim* sim, RaDev& d, bool stream = false) {
     a.dumpStride = sim->dumpStride; a.nJobs = nJobs; a.maxP = sim->maxP; a.maxR = sim->maxR;
     if (stream) {
         if (!d.hDone) {
-            RA_CUDA(sim, cudaHostAlloc(&d.hDone, sizeof(int) * (size_t)nJobs, cudaHostAllocMapped));
+            RA_CUDA(sim, cudaHostAlloc(&d.hDone, sizeof(int) * (size_t)nJobs, cudaHostAllocMapped | cudaHostAllocPortable));
             RA_CUDA(sim, cudaStreamCreateWithFlags(&d.copyStream, cudaStreamNonBlocking));
         }
         memset(d.hDone, 0, sizeof(int) * (size_t)nJobs);
@@ -854,21 +854,27 @@ extern "C" int ra_sim_run_stream(ra_sim* sim, ra_dump_cb cb, void* user) {
     if (!sim || !cb) return RA_E_INVAL;
     if (!sim->opt.dumpUEs) { sim->err = "ra_sim_run_stream needs ra_options.dumpUEs = 1 at create time"; return RA_E_STATE; }
     sim->launches = 0; sim->ran = false;
-    const int kSlots = 4;
-    struct Slot { int* rows = nullptr; ra_stats* st = nullptr; cudaEvent_t ev = nullptr; int dev = -1, job = -1; };
-    std::vector<Slot> slots(kSlots);
+    const int kSlots = 4;                                  /* staging buffers in flight per device */
+    struct Slot { int* rows = nullptr; ra_stats* st = nullptr; cudaEvent_t ev = nullptr; int job = -1; };
+    struct Ring { std::vector<Slot> slots; int head = 0, inflight = 0; std::vector<char> issued; };
+    const size_t nDev = sim->devs.size();
+    std::vector<Ring> rings(nDev);
     int rc = RA_OK;
     std::string firstErr;
     auto fail = [&](int code, const std::string& msg) { if (rc == RA_OK) { rc = code; firstErr = msg; } };
-    for (Slot& sl : slots) {
-        if (cudaHostAlloc(&sl.rows, sizeof(int) * sim->dumpStride, cudaHostAllocDefault) != cudaSuccess ||
-            cudaHostAlloc(&sl.st, sizeof(ra_stats), cudaHostAllocDefault) != cudaSuccess ||
-            cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) { fail(RA_E_NOMEM, "pinned staging buffers for the dump stream"); break; }
-    }
-    std::vector<char> launched(sim->devs.size(), 0);
-    for (size_t k = 0; k < sim->devs.size() && rc == RA_OK; ++k) {
+    std::vector<char> launched(nDev, 0);
+    for (size_t k = 0; k < nDev && rc == RA_OK; ++k) {
         RaDev& d = sim->devs[k];
         if (d.jobs.empty()) continue;
+        cudaSetDevice(d.id);                               /* events belong to the device that is current when they are made */
+        rings[k].slots.resize(kSlots);
+        rings[k].issued.assign(d.jobs.size(), 0);
+        for (Slot& sl : rings[k].slots) {
+            if (cudaHostAlloc(&sl.rows, sizeof(int) * sim->dumpStride, cudaHostAllocPortable) != cudaSuccess ||
+                cudaHostAlloc(&sl.st, sizeof(ra_stats), cudaHostAllocPortable) != cudaSuccess ||
+                cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) { fail(RA_E_NOMEM, "pinned staging buffers for the dump stream"); break; }
+        }
+        if (rc != RA_OK) break;
         d.hErr = 0;
         launched[k] = 1;
         const int lrc = ra_launch_device(sim, d, true);
@@ -876,39 +882,45 @@ extern "C" int ra_sim_run_stream(ra_sim* sim, ra_dump_cb cb, void* user) {
     }
     if (rc == RA_OK) {
         size_t total = 0, delivered = 0;
-        std::vector<std::vector<char>> issued(sim->devs.size());
-        for (size_t k = 0; k < sim->devs.size(); ++k) { issued[k].assign(sim->devs[k].jobs.size(), 0); total += sim->devs[k].jobs.size(); }
-        int head = 0, inflight = 0;                        /* slots [head, head + inflight) hold copies in issue order */
+        for (size_t k = 0; k < nDev; ++k) total += sim->devs[k].jobs.size();
         while (delivered < total && rc == RA_OK) {
             bool progress = false;
-            for (size_t k = 0; k < sim->devs.size() && inflight < kSlots; ++k) {
+            for (size_t k = 0; k < nDev && rc == RA_OK; ++k) {
+                if (!launched[k]) continue;
                 RaDev& d = sim->devs[k];
-                for (size_t j = 0; j < d.jobs.size() && inflight < kSlots; ++j) {
-                    if (issued[k][j] || !((volatile int*)d.hDone)[j]) continue;
-                    Slot& sl = slots[(head + inflight) % kSlots];
+                Ring& r = rings[k];
+                cudaSetDevice(d.id);
+                /* finished replications -> one asynchronous copy each, into the next free staging buffer */
+                for (size_t j = 0; j < d.jobs.size() && r.inflight < kSlots; ++j) {
+                    if (r.issued[j] || !((volatile int*)d.hDone)[j]) continue;
+                    Slot& sl = r.slots[(r.head + r.inflight) % kSlots];
                     const int point = d.jobs[j] / sim->reps;
-                    cudaSetDevice(d.id);
                     cudaError_t e1 = cudaMemcpyAsync(sl.rows, d.dDump + j * sim->dumpStride,
                                                      sizeof(int) * (size_t)sim->points[point].nUE * RA_DUMP_W, cudaMemcpyDeviceToHost, d.copyStream);
                     cudaError_t e2 = cudaMemcpyAsync(sl.st, d.dStats + j, sizeof(ra_stats), cudaMemcpyDeviceToHost, d.copyStream);
                     cudaError_t e3 = cudaEventRecord(sl.ev, d.copyStream);
-                    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { fail(RA_E_CUDA, "dump stream copy failed"); break; }
-                    sl.dev = (int)k; sl.job = (int)j; issued[k][j] = 1; ++inflight; progress = true;
+                    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+                        const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+                        fail(RA_E_CUDA, std::string("dump stream copy failed: ") + cudaGetErrorString(e)); break;
+                    }
+                    sl.job = (int)j; r.issued[j] = 1; ++r.inflight; progress = true;
                 }
-            }
-            while (inflight > 0 && rc == RA_OK) {
-                Slot& sl = slots[head];
-                const cudaError_t q = cudaEventQuery(sl.ev);
-                if (q == cudaErrorNotReady) break;
-                if (q != cudaSuccess) { fail(RA_E_CUDA, std::string("dump stream: ") + cudaGetErrorString(q)); break; }
-                const int gj = sim->devs[sl.dev].jobs[sl.job];
-                cb(user, gj / sim->reps, gj % sim->reps, sl.st, sl.rows);
-                head = (head + 1) % kSlots; --inflight; ++delivered; progress = true;
+                /* copies that have arrived -> the callback, in issue order */
+                while (r.inflight > 0 && rc == RA_OK) {
+                    Slot& sl = r.slots[r.head];
+                    const cudaError_t q = cudaEventQuery(sl.ev);
+                    if (q == cudaErrorNotReady) break;
+                    if (q != cudaSuccess) { fail(RA_E_CUDA, std::string("dump stream: ") + cudaGetErrorString(q)); break; }
+                    const int gj = d.jobs[sl.job];
+                    cb(user, gj / sim->reps, gj % sim->reps, sl.st, sl.rows);
+                    r.head = (r.head + 1) % kSlots; --r.inflight; ++delivered; progress = true;
+                }
             }
             if (!progress && rc == RA_OK) {
                 /* nothing finished since the last look: make sure the kernels are still healthy, then wait a little */
-                for (size_t k = 0; k < sim->devs.size(); ++k) {
+                for (size_t k = 0; k < nDev; ++k) {
                     if (!launched[k]) continue;
+                    cudaSetDevice(sim->devs[k].id);
                     const cudaError_t q = cudaStreamQuery(sim->devs[k].stream);
                     if (q != cudaSuccess && q != cudaErrorNotReady) fail(RA_E_CUDA, std::string("step kernel: ") + cudaGetErrorString(q));
                 }
@@ -917,15 +929,16 @@ extern "C" int ra_sim_run_stream(ra_sim* sim, ra_dump_cb cb, void* user) {
         }
     }
     double ms = 0;
-    for (size_t k = 0; k < sim->devs.size(); ++k) {         /* drain every launched device, also after an error */
-        if (!launched[k]) continue;
+    for (size_t k = 0; k < nDev; ++k) {                     /* drain every launched device, also after an error */
         RaDev& d = sim->devs[k];
         cudaSetDevice(d.id);
-        if (d.copyStream) cudaStreamSynchronize(d.copyStream);
-        if (rc == RA_OK) { const int crc = ra_collect_device(sim, d, &ms); if (crc != RA_OK) fail(crc, sim->err); }
-        else cudaStreamSynchronize(d.stream);
+        if (launched[k]) {
+            if (d.copyStream) cudaStreamSynchronize(d.copyStream);
+            if (rc == RA_OK) { const int crc = ra_collect_device(sim, d, &ms); if (crc != RA_OK) fail(crc, sim->err); }
+            else cudaStreamSynchronize(d.stream);
+        }
+        for (Slot& sl : rings[k].slots) { if (sl.rows) cudaFreeHost(sl.rows); if (sl.st) cudaFreeHost(sl.st); if (sl.ev) cudaEventDestroy(sl.ev); }
     }
-    for (Slot& sl : slots) { if (sl.rows) cudaFreeHost(sl.rows); if (sl.st) cudaFreeHost(sl.st); if (sl.ev) cudaEventDestroy(sl.ev); }
     if (rc != RA_OK) { sim->err = firstErr; return rc; }
     sim->kernelMs = ms; sim->ran = true;
     return RA_OK;

@@ -207,7 +207,8 @@ def test_binary_logs_and_device_list(tmp_path):
     subprocess.run([exe] + common + ["--outdir", str(tmp_path / "txt")], capture_output=True, text=True, check=True)
     devs = ",".join(str(i) for i in range(torch.cuda.device_count()))
     out_b = subprocess.run([exe] + common + ["--binlog", "--devices", devs, "--outdir", str(tmp_path / "bin")],
-                           capture_output=True, text=True, check=True)
+                           capture_output=True, text=True)
+    assert out_b.returncode == 0, out_b.stderr
     assert ("on %d device(s)" % torch.cuda.device_count()) in out_b.stderr
     for seed in range(3):
         for nue in (1200, 5000):
