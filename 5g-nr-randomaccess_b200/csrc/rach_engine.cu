@@ -710,6 +710,14 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         sim->hostPoints.push_back(pt);
         sim->arrCum.emplace_back(pt.nOcc);
         ra_host_arrcum(&p, sim->arrCum.back().data(), pt.nOcc);
+        {   /* the device reads arrivals as differences of this schedule: it must never decrease nor pass nUE */
+            const std::vector<int>& ac = sim->arrCum.back();
+            for (size_t o = 0; o < ac.size(); ++o)
+                if (ac[o] < (o ? ac[o - 1] : 0) || ac[o] > pt.nUE) {
+                    g_createErr = std::string("point ") + std::to_string(i) + ": arrival schedule is not monotone"; g_createCode = RA_E_INTERNAL;
+                    delete sim; return nullptr;
+                }
+        }
         sim->maxP = std::max(sim->maxP, pt.P); sim->maxR = std::max(sim->maxR, pt.R);
         sim->cap = std::max(sim->cap, pt.nUE);
         long long g2 = (p.variant == RA_VARIANT_N ? 24LL : 2LL) * std::min<long long>(pt.G, (long long)pt.nUE + 1) + 4;
