@@ -86,8 +86,13 @@ def table_from_files(directory, n_preamble=54):
         m = pat.match(os.path.basename(path))
         if not m:
             continue
+        vals = []
         with open(path) as f:
-            vals = [float(line.strip()) for line in f.readlines()[:6] if line.strip()]
+            for line in f.readlines()[:6]:          # B writes six numbers (B:460-482); W five, then labelled lines (W:762-793)
+                try:
+                    vals.append(float(line.strip()))
+                except ValueError:
+                    break
         if len(vals) < 5:
             continue
         vals += [0.0] * (6 - len(vals))

@@ -25,6 +25,13 @@ def test_table_from_reference_format_files(tmp_path):
             vals.setdefault(n, []).append(v)
             (tmp_path / ("%d_54_%d_Results.txt" % (seed, n))).write_text("%d\n%.2f\n%d\n%.2f\n%.2f\n%f" % tuple(v))
     (tmp_path / "0_54_UE10000_Logs.txt").write_text("not a result file")
+    # a W-format result file (W:762-793: five numbers, then labelled lines) next to the B-format ones: cumulative time 0
+    wdir = tmp_path / "w"
+    wdir.mkdir()
+    (wdir / "0_54_10000_Results.txt").write_text("10000\n100.00\n10000\n2.60\n47.10\nNumber of total preamble tx: 26000\n"
+                                                 "Finally Falied: 12\nFinally Success: 0.998801\n")
+    tw, _, cw = _ap().table_from_files(str(wdir), 54)
+    assert cw == {10000: 1} and list(tw[0]) == [10000.0, 100.0, 10000.0, 2.6, 47.1, 0.0]
     (tmp_path / "3_64_10000_Results.txt").write_text("1\n2\n3\n4\n5\n6")        # another preamble count: ignored
     table, ci, counts = _ap().table_from_files(str(tmp_path), 54)
     assert counts == {10000: 7, 20000: 7, 30000: 7} and table.shape == (3, 6)
