@@ -61,7 +61,6 @@ typedef unsigned long long ra_u64;
 #define RA_SCAP  512        /* singleton scans of one ms kept in shared memory (rest: global).  Shared memory is
                                kept small on purpose: at 5 resident blocks x 48 registers the spills live in L1 */
 #endif
-#define RA_MAGIC5 858993460u /* ra_magic(5) */
 /* Optional shared-memory front of the per-ms work lists.  Measured on B200 with 1024 / 256 entries
  * (+20 KB per block): 12 % SLOWER than leaving the lists in the block's global workspace (L2-resident):
  * the smaller L1 costs more than the shorter small phases gain.  Default: all in global memory. */
@@ -92,34 +91,41 @@ template <class T> static inline T ra_emu_min(T* p, T v) { T o = *p; if (v < o) 
 #define RA_AADD64(p, v) (*(p) += (unsigned long long)(v))
 #endif
 
-/* x % d for x < 2^31 and 1 <= d < 2^31 without a division: magic = floor(2^32/d)+1
- * (0xFFFFFFFF for d==1).  floor(x*magic/2^32) is q or q+1 for d >= 2 (error < x/2^32 < 1/2)
- * and x-1 for d == 1, so two conditional corrections make the remainder exact. */
-RA_HD unsigned ra_magic(unsigned d) { return d <= 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ull / d) + 1u; }
-RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic) {
-    unsigned q = rach_mulhi32(x, magic);
-    int r = (int)(x - q * d);
-    if (r < 0) r += (int)d;
-    if (r >= (int)d) r -= (int)d;
-    return (unsigned)r;
+/* x % d for x < 2^31 and 1 <= d <= 2^16 without a division.  With l = ceil(log2 d), magic = floor(2^(31+l) / d) + 1 fits
+ * in 32 bits and floor(x * magic / 2^(31+l)) is exactly x / d: magic = 2^(31+l)/d + e with 0 < e <= 1, so the product
+ * overshoots x/d by x*e / 2^(31+l) < 2^-l <= 1/d, which cannot carry x/d = q + r/d (r <= d-1) past q + 1.  The quotient is
+ * (x * magic >> 32) >> (l - 1).  d == 1 (l = 0) takes magic = 0xFFFFFFFF, shift 0: the quotient comes out as x - 1 and the
+ * one conditional subtraction below makes the remainder 0. */
+RA_HD unsigned ra_mod_shift(unsigned d) { unsigned l = 0; while ((1u << l) < d) ++l; return l ? l - 1 : 0; }
+RA_HD unsigned ra_magic(unsigned d) {
+    if (d <= 1) return 0xFFFFFFFFu;
+    unsigned l = 0; while ((1u << l) < d) ++l;
+    return (unsigned)((1ull << (31 + l)) / d) + 1u;
+}
+RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic, unsigned shift) {
+    const unsigned q = rach_mulhi32(x, magic) >> shift;
+    unsigned r = x - q * d;
+    if (r >= d) r -= d;
+    return r;
 }
 
 /* ---- one parameter point, device view ---------------------------------------------------- */
 struct RaPointDev {
     int nUE, P, BI, G, Wn, M, A, maxTime;
     int geometry, R, nOcc, hshift;  /* hshift: idx >> hshift < RA_HBINS */
-    unsigned magicBI, magicP, magicA;      /* ra_magic() of the three runtime divisors */
+    unsigned magicBI, magicP, magicA;      /* ra_magic() of the three runtime divisors (shifts: modSh) */
     float cellRadius;                      /* variant N: per point (N:56, used by activeUE N:168) */
     ra_u64 seed;
     const int* arrCum;        /* [nOcc] activeCheck after the arrival step of ms occ*A (W:280-292) */
     /* byte offsets of the block's tables in dynamic shared memory (ra_layout): a function of (R, P) only, kept
      * here so that a launch whose replications share one point reads them as kernel constants */
     unsigned oMinI, oCnt, oBcount, oM3count, oN, oL1, oNlList, oL1m, oL2, oBefore, oExtraFirst, oClsSize;
-    unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes, oDead, padO;
+    unsigned oHist, oSIdx, oSLand, oSLandMeta, oSUnc, smemBytes, oDead;
+    unsigned modSh;                        /* ra_mod_shift() of BI | P << 8 | A << 16 */
     /* rand() % backoffIndicator (W:514,540,685), rand() % nPreamble (W:478,502,701), subTime % accessTime (W:518) */
-    RA_HDM unsigned modBI(unsigned x) const { return ra_mod(x, (unsigned)BI, magicBI); }
-    RA_HDM unsigned modP(unsigned x) const { return ra_mod(x, (unsigned)P, magicP); }
-    RA_HDM unsigned modA(unsigned x) const { return ra_mod(x, (unsigned)A, magicA); }
+    RA_HDM unsigned modBI(unsigned x) const { return ra_mod(x, (unsigned)BI, magicBI, modSh & 0xFFu); }
+    RA_HDM unsigned modP(unsigned x) const { return ra_mod(x, (unsigned)P, magicP, (modSh >> 8) & 0xFFu); }
+    RA_HDM unsigned modA(unsigned x) const { return ra_mod(x, (unsigned)A, magicA, modSh >> 16); }
 };
 
 /* table layout for (R, P); 16-byte records first.  One definition for the runtime point (ra_layout) and for the
@@ -232,11 +238,11 @@ RA_HD unsigned ra_rec_fail(const uint4& r) { return r.z >> 16; }
 RA_HD unsigned ra_z(unsigned ts, unsigned fail) { return (ts & 0xFFFFu) | (fail << 16); }
 
 /* slot alignment, W:518-527 (= W:544-553, W:688-697) */
-RA_HD int ra_align(int subTime, int A, unsigned magicA) {
-    int r = (int)ra_mod((unsigned)subTime, (unsigned)A, magicA);
+RA_HD int ra_align5(int subTime) {                       /* the literal 5 of the Msg3 restart, W:687-697 */
+    const int r = (int)((unsigned)subTime % 5u);
     if (r == 0) return subTime + 1;
     if (r == 1) return subTime;
-    return subTime + (A - r + 1);
+    return subTime + (5 - r + 1);
 }
 
 template <class PT>
@@ -326,7 +332,11 @@ RA_HD unsigned ra_bucket_push(const PT& pt, const RaWork& w, RaShared& s, int m,
      * per bucket with __match_any_sync (the variable-mask shuffle that follows costs more than the contention) */
     unsigned pos = RA_AADD(&S_bcount[slot], 1u);
     if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
+#if defined(__CUDA_ARCH__) && defined(RA_STREAM_HINTS)
+    __stcs(reinterpret_cast<::uint4*>(&w.bucket[(size_t)slot * w.cap + pos]), rec);     /* written once, read once, much later */
+#else
     w.bucket[(size_t)slot * w.cap + pos] = rec;
+#endif
     return pos;
 }
 
@@ -433,7 +443,7 @@ template <class PT>
 RA_HD void ra_phase0_ctl(const RaJobT<PT>& job, RaShared& s, int T) {
     const PT& pt = *job.pt;
     const unsigned Rm = (unsigned)(pt.R - 1);
-    if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) s.grantCheck = 0;          /* literal 5, W:268 */
+    if ((unsigned)T % 5u == 0) s.grantCheck = 0;          /* literal 5, W:268 */
     s.nLanders = 0; s.nUnc = 0; s.nC3 = 0; s.nSingles = 0; s.nE1 = 0; s.tau = RA_INF32; s.noGrant = 0; s.nNl = 0;
     s.acOld = s.activeCheck;
     if (T == s.nextArrMs) {                                                 /* T % accessTime == 0, W:280 */
@@ -564,7 +574,7 @@ RA_HD int ra_msg3_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAc
     /* 48 ms later: full restart, W:682-708 (accessTime is the literal 5, W:687) */
     acc.contFailed++;
     int tmp = (int)pt.modBI(d.v[0] >> 1);
-    int X = ra_align(T + tmp, 5, RA_MAGIC5);
+    int X = ra_align5(T + tmp);
     unsigned pnew = pt.modP(d.v[1] >> 1);
     unsigned fail = ra_rec_fail(rec) + 1;
     if (fail > 0xFFFFu) s.overflow = 2;
@@ -931,7 +941,7 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
     const unsigned nArr = (unsigned)(newAc - c.activeCheck), nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
     if (nArr + nM3 > 32u) return 0;
     /* control block of ms T (ra_phase0_ctl on registers) */
-    if (ra_mod((unsigned)T, 5u, RA_MAGIC5) == 0) c.grantCheck = 0;          /* literal 5, W:268 */
+    if ((unsigned)T % 5u == 0) c.grantCheck = 0;          /* literal 5, W:268 */
     const unsigned acOld = (unsigned)c.activeCheck;
     c.activeCheck = newAc;
     if (arrivalMs) {

@@ -152,7 +152,7 @@ RA_HD void rn_phaseA1_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int
     const float cellRadius = pt.cellRadius;
     RaStream st = ra_stream(job, idx, T);
     const float pi = 3.14;
-    const unsigned p = ra_mod((unsigned)ra_stream_next(st), (unsigned)pt.P, pt.magicP);            /* N:133 */
+    const unsigned p = pt.modP((unsigned)ra_stream_next(st));            /* N:133 */
     const int ra = ra_stream_next(st);                                                             /* N:142 */
     const float angle = (float)ra / (float)(2147483647) * 2 * pi;
     const int sector = ra_sector(ra);                                                              /* N:146-163 */
@@ -346,10 +346,10 @@ RA_HD void rn_phaseC_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int 
     /* msg2 == 0: rarWindow = 5 >= maxRarWindow -> retransmission, N:452-479 */
     unsigned nTx = rn_ntx(r) + 1, reTx = rn_retx(r) + 1;
     const rach_u32x4 d = ra_draws(job, idx, T + 1);
-    const int tmp = (int)ra_mod(d.v[0] >> 1, (unsigned)pt.BI, pt.magicBI);
-    const int X = ra_align(T + 1 + 3 + tmp, pt.A, pt.magicA);
+    const int tmp = (int)pt.modBI(d.v[0] >> 1);
+    const int X = ra_align_pt(pt, T + 1 + 3 + tmp);
     if ((int)reTx >= pt.M) {                                /* N:481-488: dropped for good */
-        const unsigned pnew = ra_mod(d.v[1] >> 1, (unsigned)pt.P, pt.magicP);
+        const unsigned pnew = pt.modP(d.v[1] >> 1);
         RA_AADD(&s.nDropped, 1u);
         if (DUMP) {
             int* row = job.dump + (size_t)idx * RA_DUMP_W;
@@ -391,9 +391,9 @@ RA_HD void rn_msg3_item(const RaJob& job, const RaWorkN& w, RaSharedN& s, int T,
         return;
     }
     /* restart, N:514-543: new preamble first (N:519), then the backoff draw (N:520) */
-    const unsigned pnew = ra_mod(d.v[0] >> 1, (unsigned)pt.P, pt.magicP);
-    const int tmp = (int)ra_mod(d.v[1] >> 1, (unsigned)pt.BI, pt.magicBI);
-    const int X = ra_align(T + tmp, pt.A, pt.magicA);
+    const unsigned pnew = pt.modP(d.v[0] >> 1);
+    const int tmp = (int)pt.modBI(d.v[1] >> 1);
+    const int X = ra_align_pt(pt, T + tmp);
     unsigned m3f = rn_m3f(r) + 1;
     if (m3f > 0xFFu) s.overflow = 2;
     const uint4 nr = make_uint4(idx, (unsigned)X, rn_z((unsigned)T, 0, 0), rn_w(pnew, rn_sector(r), m3f, 1, 0));

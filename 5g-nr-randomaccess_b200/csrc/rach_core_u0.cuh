@@ -58,16 +58,16 @@ RA_HD int ru_select(const RaJob& job, RuUE& u, int time, unsigned& k) {
     int dropped = 0;
     if (u.active == 1 && u.msg2Flag == 0) {
         if (u.preamble == -1) {
-            u.preamble = (int)ra_mod((unsigned)ru_rand(job, u, time, k), (unsigned)pt.P, pt.magicP);
+            u.preamble = (int)pt.modP((unsigned)ru_rand(job, u, time, k));
             u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter = 0; u.preambleChange = 1;
         } else if (u.nowBackoff == 0) {
             u.rarWindow++;
             if (u.rarWindow >= 5) {
-                int tmp = (int)ra_mod((unsigned)ru_rand(job, u, time, k), (unsigned)pt.BI, pt.magicBI) + 2;
+                int tmp = (int)pt.modBI((unsigned)ru_rand(job, u, time, k)) + 2;
                 u.txTime = time + tmp; u.nowBackoff = tmp; u.rarWindow = 0; u.maxRarCounter++;
                 if (u.maxRarCounter >= 10) {
                     u.raFailed = -1; dropped = 1;
-                    u.preamble = (int)ra_mod((unsigned)ru_rand(job, u, time, k), (unsigned)pt.P, pt.magicP);
+                    u.preamble = (int)pt.modP((unsigned)ru_rand(job, u, time, k));
                     u.maxRarCounter = 0; u.preambleChange++;
                 }
             }
@@ -93,8 +93,8 @@ RA_HD int ru_msg3_timer(const RaJob& job, RuUE& u, int time, unsigned& k) {
             else u.txTime = time + 1;
         } else {
             u.active = 1;
-            u.txTime = time + (int)ra_mod((unsigned)ru_rand(job, u, time, k), (unsigned)pt.BI, pt.magicBI) + 2;
-            u.preamble = (int)ra_mod((unsigned)ru_rand(job, u, time, k), (unsigned)pt.P, pt.magicP);
+            u.txTime = time + (int)pt.modBI((unsigned)ru_rand(job, u, time, k)) + 2;
+            u.preamble = (int)pt.modP((unsigned)ru_rand(job, u, time, k));
             u.msg2Flag = 0; u.rarWindow = 0; u.maxRarCounter = 0; u.preambleTxCounter++;
         }
     }

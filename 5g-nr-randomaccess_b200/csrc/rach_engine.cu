@@ -56,6 +56,11 @@
 #define RA_MINB_N 8        /* round 2): 128 x 8 57.0 ms, 96 x 10 57.5 ms, 192 x 5 63.6 ms, 256 x 4 76.2 ms (round 1, one lane per
                               sector: 192 x 5 169 ms) */
 #endif
+#ifdef RA_STREAM_HINTS
+#define RA_LDREC(p) __ldcs(p)        /* bucket records are read exactly once: streaming (evict-first) loads */
+#else
+#define RA_LDREC(p) (*(p))
+#endif
 #define RA_NPHASE 10
 #ifndef RA_LIGHT
 #define RA_LIGHT 1           /* 0: every ms takes the general (block-wide) path -- for cross-checks and A/B timing */
@@ -169,12 +174,12 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                 int left = (int)nMov - tid;
                 uint4 c[RA_ILP];
 #pragma unroll
-                for (int k = 0; k < RA_ILP; ++k) c[k] = left > k * NT ? pr[k * NT] : dead;
+                for (int k = 0; k < RA_ILP; ++k) c[k] = left > k * NT ? RA_LDREC(&pr[k * NT]) : dead;
                 while (left > 0) {
                     uint4 n[RA_ILP];
                     rach_u32x4 d[RA_ILP];
 #pragma unroll
-                    for (int k = 0; k < RA_ILP; ++k) n[k] = left > (RA_ILP + k) * NT ? pr[(RA_ILP + k) * NT] : dead;
+                    for (int k = 0; k < RA_ILP; ++k) n[k] = left > (RA_ILP + k) * NT ? RA_LDREC(&pr[(RA_ILP + k) * NT]) : dead;
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) d[k] = ra_draws(job, c[k].x, T);
 #pragma unroll

@@ -162,6 +162,7 @@ void ra_host_fill_point(RaPointDev* pt) {
     pt->magicBI = ra_magic((unsigned)pt->BI);
     pt->magicP = ra_magic((unsigned)pt->P);
     pt->magicA = ra_magic((unsigned)pt->A);
+    pt->modSh = ra_mod_shift((unsigned)pt->BI) | (ra_mod_shift((unsigned)pt->P) << 8) | (ra_mod_shift((unsigned)pt->A) << 16);
     int sh = 0;
     while (((pt->nUE - 1) >> sh) >= RA_HBINS) ++sh;
     pt->hshift = sh;

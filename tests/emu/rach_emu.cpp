@@ -261,3 +261,6 @@ extern "C" int emu_run_u0(const ref_config* cfg, ref_result* res, int* perUE, fl
     res->continueFailed = st.dropped; res->captured = 1;
     return st.overflow ? -3 : 0;
 }
+
+/* the engine's division-free modulo (rach_core.cuh: ra_magic / ra_mod_shift / ra_mod), for the exactness test */
+extern "C" unsigned emu_mod(unsigned x, unsigned d) { return ra_mod(x, d, ra_magic(d), ra_mod_shift(d)); }

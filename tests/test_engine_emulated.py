@@ -197,3 +197,21 @@ def test_light_ms_path_against_general_path(oracle, emu):
             assert getattr(out[0][0], k) == getattr(out[1][0], k), (k, kw)
         np.testing.assert_array_equal(out[0][1], out[1][1], err_msg=str(kw))
     assert n_code2.value > 0
+
+
+def test_division_free_modulo_is_exact():
+    """rand() % backoffIndicator, rand() % nPreamble, subTime % accessTime (W:478,502,514,518) run as multiply-shift with a
+    per-divisor magic number (rach_core.cuh: ra_magic / ra_mod_shift / ra_mod).  Exact for every divisor the validator
+    admits (<= 4096) and beyond, over the whole 31-bit range of rand(): edge values around multiples + random ones."""
+    so = subprocess.check_output([os.path.join(ROOT, "tests", "emu", "build_emu.sh")]).decode().strip()
+    lib = C.CDLL(so)
+    lib.emu_mod.restype = C.c_uint
+    lib.emu_mod.argtypes = [C.c_uint, C.c_uint]
+    rnd = random.Random(1)
+    top = 2 ** 31 - 1
+    for d in list(range(1, 4100)) + [5000, 8191, 8192, 8193, 65535, 65536]:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, top, top - 1, top // d * d, top // d * d - 1]
+        xs += [rnd.randrange(2 ** 31) for _ in range(30)]
+        for x in xs:
+            if 0 <= x <= top:
+                assert lib.emu_mod(x, d) == x % d, (x, d)
