@@ -56,11 +56,6 @@
 #define RA_MINB_N 8        /* round 2): 128 x 8 57.0 ms, 96 x 10 57.5 ms, 192 x 5 63.6 ms, 256 x 4 76.2 ms (round 1, one lane per
                               sector: 192 x 5 169 ms) */
 #endif
-#ifdef RA_STREAM_HINTS
-#define RA_LDREC(p) __ldcs(p)        /* bucket records are read exactly once: streaming (evict-first) loads */
-#else
-#define RA_LDREC(p) (*(p))
-#endif
 #define RA_NPHASE 10
 #ifndef RA_LIGHT
 #define RA_LIGHT 1           /* 0: every ms takes the general (block-wide) path -- for cross-checks and A/B timing */
