@@ -290,6 +290,14 @@ RA_HD int ra_align_pt(const PT& pt, int subTime) {
     return subTime + (pt.A - r + 1);
 }
 
+/* the same with a compile-time subframe A >= 2: the first ms congruent to 1 (mod A) at or after subTime -- one
+ * multiply-shift division, no branch (r == 0 -> +1, r == 1 -> +0, else +(A - r + 1), all of them A * floor((subTime + A - 2) / A) + 1) */
+template <int P_, int BI_, int A_, int Wn_, int R_>
+RA_HD int ra_align_pt(const RaPointFixed<P_, BI_, A_, Wn_, R_>&, int subTime) {
+    if (A_ >= 2) return (int)(((unsigned)subTime + (unsigned)(A_ - 2)) / (unsigned)A_ * (unsigned)A_) + 1;
+    return subTime + 1;
+}
+
 template <class PT>
 RA_HD rach_u32x4 ra_draws(const RaJobT<PT>& job, unsigned ue, int ms) {
     return rach_tape_block(job.pt->seed, job.rep, ue, (unsigned)ms, 0u, RACH_TAPE_TAG_UE);
@@ -369,7 +377,7 @@ RA_HD unsigned ra_bucket_push(const PT& pt, const RaWork& w, RaShared& s, int m,
      * per bucket with __match_any_sync (the variable-mask shuffle that follows costs more than the contention) */
     unsigned pos = RA_AADD(&S_bcount[slot], 1u);
     if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
-    RA_STREC(&w.bucket[(size_t)slot * w.cap + pos], rec);
+    RA_STREC(&w.bucket[slot * (unsigned)w.cap + pos], rec);      /* ring x capacity < 2^32 records (checked at create) */
     return pos;
 }
 
@@ -505,20 +513,45 @@ RA_HD void ra_phase0(const RaJobT<PT>& job, RaShared& s, int T, int tid, int nt)
  *   [nMov, +nArr)        arrivals: activateUEs + first selectPreamble, W:294-298,383-394,477-487
  *   [.., +nM3)           Msg3 due: requestResourceAllocation, W:667-710
  * ========================================================================================= */
-template <bool DUMP, class PT>
-RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d);
+/* A mover that re-transmits in this very ms (backoff draw 0 on a tx slot, W:540-549: one mover in twenty) joins the
+ * ms' work list of re-transmitters.  Done on the spot that is a 40-instruction branch which three of four warp
+ * iterations enter for a single lane (measured: 14 % of the step kernel's warp instructions at 1 of 32 lanes).  So the
+ * mover only parks the record in its thread's registers (RaPend) and the thread puts it on the list later -- the
+ * kernel when two of them meet in one lane of the warp (then every lane of the warp flushes) and at the end of the
+ * bucket.  The list has no order (entries are appended by atomics), so when an entry gets there is immaterial as long
+ * as it is before the barrier that ends phase 1. */
+struct RaPend { unsigned x, z, w; };      /* x = idx | member << 31 (idx < 2^24), RA_INF32 = empty; z, w as in the record */
 
-template <bool DUMP, class PT>
-RA_HD void ra_phase1_mover(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec) {
-    if (rec.x == RA_DEAD) return;
-    ra_phase1_mover_d<DUMP>(job, w, s, acc, T, item, rec, ra_draws(job, rec.x, T));
+template <class PT>
+RA_HD void ra_pend_flush(const PT& pt, const RaWork& w, RaShared& s, int T, RaPend& pd) {
+    if (pd.x == RA_INF32) return;
+    const unsigned idx = pd.x & 0x7FFFFFFFu;
+    RA_AMIN(&S_l2[pd.w & 0xFFu], idx);
+    ra_lander_push(pt, w, s, make_uint4(idx, (unsigned)T, pd.z, pd.w), pd.x >> 31);
+    pd.x = RA_INF32;
 }
 
-/* the draws of (UE, T) are passed in so that the kernel can run two Philox chains side by side */
 template <bool DUMP, class PT>
-RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d) {
-    const PT& pt = *job.pt;
+RA_HD bool ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d, RaPend& land);
+
+/* one mover, its re-transmission (if any) parked in `pd` (the caller flushes it before the phase ends) */
+template <bool DUMP, class PT>
+RA_HD void ra_phase1_mover(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, RaPend& pd) {
     if (rec.x == RA_DEAD) return;
+    RaPend land;
+    if (ra_phase1_mover_d<DUMP>(job, w, s, acc, T, item, rec, ra_draws(job, rec.x, T), land)) {
+        ra_pend_flush(*job.pt, w, s, T, pd);
+        pd = land;
+    }
+}
+
+/* the draws of (UE, T) are passed in so that the kernel can run two Philox chains side by side.  Returns true if the
+ * UE re-transmits in this ms: its new record is then in `land` and has NOT been put on the work list. */
+template <bool DUMP, class PT>
+RA_HD bool ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaAcc& acc, int T, unsigned item, const uint4& rec, const rach_u32x4& d, RaPend& land) {
+    const PT& pt = *job.pt;
+    land.x = RA_INF32; land.z = 0; land.w = 0;
+    if (rec.x == RA_DEAD) return false;
     const unsigned idx = rec.x, p0 = ra_rec_p(rec), stale = ra_rec_flag(rec);
     /* below the lowest visible non-mover of my class: nobody is sure to have postponed me */
     const bool uncertain = !stale && idx < S_l1[p0];
@@ -544,23 +577,25 @@ RA_HD void ra_phase1_mover_d(const RaJobT<PT>& job, const RaWork& w, RaShared& s
     if (limit ? rec.z >= 0xFFFF0000u : (wRetry >> 31) != 0u) s.overflow = 2;
     const int X = ra_align_pt(pt, base + tmp);
     const uint4 nr = make_uint4(idx, (unsigned)X, z, nw);
+    land.z = z; land.w = nw;                               /* (assigned on every path: the values stay in registers) */
     if (uncertain) {
         unsigned u = RA_AADD(&s.nUnc, 1u);
         ra_unc_set(pt, w, u, make_uint4(item, idx, p0 | (limit ? 0x80000000u : 0u), 0));
         if (limit) {
             if (X == T) { unsigned c = RA_AADD(&s.nC3, 1u); w.c3[c] = make_uint4(idx, p0, pnew, 0); }
-            return;
+            return false;
         }
     }
     if (DUMP) job.dump[(size_t)idx * RA_DUMP_W + (limit ? 3 : 4)] = limit ? T + 1 : X;   /* W:510 / W:557 */
     if (X > T) {
         ra_schedule(pt, w, s, nr);                          /* the common case, one call site */
-    } else if (X == T) {                                    /* backoff 0 on a tx slot: transmits now */
-        RA_AMIN(&S_l2[pnew], idx);
-        ra_lander_push(pt, w, s, nr, (!stale && !limit) ? 1u : 0u);
+    } else if (X == T) {                                    /* backoff 0 on a tx slot: transmits now (class pnew = nw & 0xFF) */
+        land.x = idx | ((!stale && !limit) ? 0x80000000u : 0u);
+        return true;
     } else {
         ra_park_stale(pt, w, s, T, nr);                     /* only from an old txTime */
     }
+    return false;
 }
 
 /* arrival of UE idx, W:383-394 + first draw W:477-487 */
@@ -626,7 +661,9 @@ RA_HD void ra_phase1_item(const RaJobT<PT>& job, const RaWork& w, RaShared& s, R
     const PT& pt = *job.pt;
     const unsigned Rm = (unsigned)(pt.R - 1);
     if (item < s.nMov) {
-        ra_phase1_mover<DUMP>(job, w, s, acc, T, item, w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item]);
+        RaPend pd; pd.x = RA_INF32; pd.z = pd.w = 0;
+        ra_phase1_mover<DUMP>(job, w, s, acc, T, item, w.bucket[(size_t)((unsigned)T & Rm) * w.cap + item], pd);
+        ra_pend_flush(pt, w, s, T, pd);
         return;
     }
     item -= s.nMov;

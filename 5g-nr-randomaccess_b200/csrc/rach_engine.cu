@@ -60,6 +60,9 @@
 #ifndef RA_LIGHT
 #define RA_LIGHT 1           /* 0: every ms takes the general (block-wide) path -- for cross-checks and A/B timing */
 #endif
+#ifndef RA_DEFER
+#define RA_DEFER 1           /* 1: re-transmitters of the ms wait in registers and reach the work list a warp at a time (RaPend) */
+#endif
 #ifndef RA_ILP
 #define RA_ILP 2             /* movers per thread and loop iteration (interleaved Philox chains) */
 #endif
@@ -167,10 +170,14 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                  * immediate offsets), `left` = records from the thread's current one to the end of the bucket */
                 const uint4* pr = bT + tid;
                 int left = (int)nMov - tid;
+                /* the trip count is the warp's (that of its first lane; lanes past the end of the bucket carry dead
+                 * records): the warp votes inside the loop */
+                int leftW = (int)nMov - (tid & ~31);
+                RaPend pd; pd.x = RA_INF32; pd.z = pd.w = 0;      /* this thread's parked re-transmitter (ra_pend_flush) */
                 uint4 c[RA_ILP];
 #pragma unroll
                 for (int k = 0; k < RA_ILP; ++k) c[k] = left > k * NT ? RA_LDREC(&pr[k * NT]) : dead;
-                while (left > 0) {
+                while (leftW > 0) {
                     uint4 n[RA_ILP];
                     rach_u32x4 d[RA_ILP];
 #pragma unroll
@@ -178,19 +185,33 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) d[k] = ra_draws(job, c[k].x, T);
 #pragma unroll
-                    for (int k = 0; k < RA_ILP; ++k) ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * NT, c[k], d[k]);
+                    for (int k = 0; k < RA_ILP; ++k) {
+                        RaPend land;
+                        const bool lands = ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * NT, c[k], d[k], land);
+#if RA_DEFER
+                        /* a second re-transmitter in a lane that still holds one: the whole warp empties its registers
+                         * (one pass of the list code for a dozen lanes instead of one pass per lane) */
+                        if (__any_sync(0xFFFFFFFFu, lands && pd.x != RA_INF32)) ra_pend_flush(pt, w, s, T, pd);
+                        if (lands) pd = land;
+#else
+                        if (lands) { pd = land; ra_pend_flush(pt, w, s, T, pd); }
+#endif
+                    }
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) c[k] = n[k];
-                    i += RA_ILP * NT; pr += RA_ILP * NT; left -= RA_ILP * NT;
+                    i += RA_ILP * NT; pr += RA_ILP * NT; left -= RA_ILP * NT; leftW -= RA_ILP * NT;
                 }
+                ra_pend_flush(pt, w, s, T, pd);
 #else
                 uint4 c0 = i < nMov ? bT[i] : dead;
+                RaPend pd; pd.x = RA_INF32; pd.z = pd.w = 0;
                 while (i < nMov) {
                     const unsigned ni = i + nt;
                     const uint4 n0 = ni < nMov ? bT[ni] : dead;
-                    ra_phase1_mover<DUMP>(job, w, s, acc, T, i, c0);
+                    ra_phase1_mover<DUMP>(job, w, s, acc, T, i, c0, pd);
                     c0 = n0; i = ni;
                 }
+                ra_pend_flush(pt, w, s, T, pd);
 #endif
                 const unsigned n1 = nMov + (unsigned)s.nArr + s.nM3;
                 for (i = nMov + tid; i < n1; i += nt) ra_phase1_item<DUMP>(job, w, s, acc, T, i);
@@ -723,6 +744,10 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
         long long g2 = (p.variant == RA_VARIANT_N ? 24LL : 2LL) * std::min<long long>(pt.G, (long long)pt.nUE + 1) + 4;
         sim->cap3 = std::max<long long>(sim->cap3, g2);
         sim->dumpStride = std::max(sim->dumpStride, (size_t)pt.nUE * RA_DUMP_W);
+    }
+    /* the engines index a block's move calendar with 32 bits (ring x capacity records of 16 bytes: 64 GB) */
+    if ((unsigned long long)sim->maxR * (unsigned long long)sim->cap >= (1ull << 32)) {
+        g_createErr = "ring x nUE exceeds 2^32 calendar records per replication"; g_createCode = RA_E_INVAL; delete sim; return nullptr;
     }
     std::vector<int> devs;
     if (!devices || nDevices < 1) devs.push_back(0);

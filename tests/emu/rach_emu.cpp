@@ -55,7 +55,16 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
         if (code == 0) {
             for (int t = 0; t < 32; ++t) ra_phase0(job, s, T, t, 32);
             unsigned n1 = s.nMov + (unsigned)s.nArr + s.nM3;
-            for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
+            /* as in the kernel: a thread walks its movers first, a re-transmitter among them waits in the thread's RaPend until
+             * the next one arrives or the bucket ends; then the arrivals and Msg3 answers */
+            const uint4* bT = w.bucket + (size_t)((unsigned)T & (unsigned)(pt.R - 1)) * w.cap;
+            for (int t = 0; t < NT; ++t) {
+                RaPend pd; pd.x = RA_INF32; pd.z = pd.w = 0;
+                unsigned i = t;
+                for (; i < s.nMov; i += NT) ra_phase1_mover<DUMP>(job, w, s, acc[t], T, i, bT[i], pd);
+                ra_pend_flush(pt, w, s, T, pd);
+                for (; i < n1; i += NT) ra_phase1_item<DUMP>(job, w, s, acc[t], T, i);
+            }
         } else if (code == 2) {
             for (int t = 0; t < 32; ++t) ra_phase0_classes(job, s, T, t, 32);
         }
