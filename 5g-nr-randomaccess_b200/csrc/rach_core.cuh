@@ -112,6 +112,16 @@ RA_HD unsigned ra_mod(unsigned x, unsigned d, unsigned magic, unsigned shift) {
 /* A calendar record is written once and read once, several ms later, by which time a thousand other replications have been
  * through the caches: streaming (evict-first) stores and loads keep the 16-byte records from displacing what IS re-used
  * (work lists, position hints).  Measured on the bench workload: 965 -> 945 ms. */
+/* tuning switches of the mover path (A/B timings in profiles/r02j_*) */
+#ifndef RA_IDX32
+#define RA_IDX32 1          /* 32-bit record index into the move calendar */
+#endif
+#ifndef RA_ALIGN_CLOSED
+#define RA_ALIGN_CLOSED 1   /* branch-free slot alignment for a compile-time subframe */
+#endif
+#ifndef RA_MIN_PLAIN_FIRST
+#define RA_MIN_PLAIN_FIRST 0   /* 1: read the cohort minimum first and only then atomicMin (measured 0.6 % slower than the bare atomic) */
+#endif
 #ifndef RA_LD_HINT
 #define RA_LD_HINT 1        /* 0 plain, 1 ld.global.cs (streaming), 2 ld.global.lu (last use) */
 #endif
@@ -294,8 +304,15 @@ RA_HD int ra_align_pt(const PT& pt, int subTime) {
  * multiply-shift division, no branch (r == 0 -> +1, r == 1 -> +0, else +(A - r + 1), all of them A * floor((subTime + A - 2) / A) + 1) */
 template <int P_, int BI_, int A_, int Wn_, int R_>
 RA_HD int ra_align_pt(const RaPointFixed<P_, BI_, A_, Wn_, R_>&, int subTime) {
+#if RA_ALIGN_CLOSED
     if (A_ >= 2) return (int)(((unsigned)subTime + (unsigned)(A_ - 2)) / (unsigned)A_ * (unsigned)A_) + 1;
     return subTime + 1;
+#else
+    const int r = (int)((unsigned)subTime % (unsigned)A_);
+    if (r == 0) return subTime + 1;
+    if (r == 1) return subTime;
+    return subTime + (A_ - r + 1);
+#endif
 }
 
 template <class PT>
@@ -377,7 +394,11 @@ RA_HD unsigned ra_bucket_push(const PT& pt, const RaWork& w, RaShared& s, int m,
      * per bucket with __match_any_sync (the variable-mask shuffle that follows costs more than the contention) */
     unsigned pos = RA_AADD(&S_bcount[slot], 1u);
     if (pos >= (unsigned)w.cap) { s.overflow = 1; return 0; }
+#if RA_IDX32
     RA_STREC(&w.bucket[slot * (unsigned)w.cap + pos], rec);      /* ring x capacity < 2^32 records (checked at create) */
+#else
+    RA_STREC(&w.bucket[(size_t)slot * w.cap + pos], rec);
+#endif
     return pos;
 }
 
@@ -389,9 +410,13 @@ RA_HD void ra_schedule(const PT& pt, const RaWork& w, RaShared& s, const uint4& 
     const unsigned pos = ra_bucket_push(pt, w, s, m, rec);
     unsigned c = ((unsigned)m & (unsigned)(pt.R - 1)) * (unsigned)pt.P + ra_rec_p(rec);
     RA_AADD(&S_cnt[c], 1u);
+#if RA_MIN_PLAIN_FIRST
     if (rec.x < S_minI[c]) {                              /* plain read first: the minimum rarely moves */
         if (RA_AMIN(&S_minI[c], rec.x) > rec.x) w.minPos[c] = pos;
     }
+#else
+    if (RA_AMIN(&S_minI[c], rec.x) > rec.x) w.minPos[c] = pos;
+#endif
 }
 
 /* a UE whose txTime is not in the future and that nobody postpones (W:516 applied to an old

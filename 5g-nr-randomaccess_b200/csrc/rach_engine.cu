@@ -63,6 +63,9 @@
 #ifndef RA_DEFER
 #define RA_DEFER 1           /* 1: re-transmitters of the ms wait in registers and reach the work list a warp at a time (RaPend) */
 #endif
+#ifndef RA_LOOP_UNROLL
+#define RA_LOOP_UNROLL 1
+#endif
 #ifndef RA_ILP
 #define RA_ILP 2             /* movers per thread and loop iteration (interleaved Philox chains) */
 #endif
@@ -177,6 +180,9 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                 uint4 c[RA_ILP];
 #pragma unroll
                 for (int k = 0; k < RA_ILP; ++k) c[k] = left > k * NT ? RA_LDREC(&pr[k * NT]) : dead;
+#if RA_LOOP_UNROLL == 2
+#pragma unroll 2
+#endif
                 while (leftW > 0) {
                     uint4 n[RA_ILP];
                     rach_u32x4 d[RA_ILP];
