@@ -1029,8 +1029,18 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
     const PT& pt = *job.pt;
     const int P = pt.P, Wn = pt.Wn;
     const unsigned Rm = (unsigned)(pt.R - 1), slotT = (unsigned)T & Rm;
-    /* eligibility: no state is touched before the ms is known to be light */
-    if (S_bcount[slotT] != S_dead[slotT]) return 0;
+    /* eligibility: no state is touched before the ms is known to be light.  One ballot answers it together with the
+     * question the class view asks below -- which cohorts of the window [T, T+Wn-1] have a live record at all (lane d
+     * looks at the bucket of T+d; bit 0 = bucket T itself).  The events of this ms cannot change the answer: an arrival
+     * or a Msg3 restart transmits at T+1 or later and so joins the cohort of T+Wn or later. */
+    const bool canSkip = Wn <= 32;                          /* one bit per cohort of the window */
+    unsigned liveWin = 0;
+    if (canSkip) {
+        int lv[RW_LANES];
+        RW_EACH(l) { const unsigned m = ((unsigned)(T + lane) & Rm); lv[l] = lane < Wn && S_bcount[m] != S_dead[m]; }
+        liveWin = RW_BALLOT(lv);
+        if (liveWin & 1u) return 0;
+    } else if (S_bcount[slotT] != S_dead[slotT]) return 0;
     const bool arrivalMs = T == c.nextArrMs;
     const int newAc = (arrivalMs && c.activeCheck != pt.nUE) ? c.nextAc : c.activeCheck;
     const unsigned nArr = (unsigned)(newAc - c.activeCheck), nM3 = S_m3count[(unsigned)T & (RA_M3RING - 1)];
@@ -1057,10 +1067,7 @@ RW_FN int ra_light_ms(const RaJobT<PT>& job, const RaWork& w, RaShared& s, RaCtl
     /* phases 0 + 4 fused: the class view, and the one scan per visible class (no mover, no re-transmitter, nobody left
      * early: size = N, first scan by the lowest visible index).  A cohort whose bucket holds no live record (empty, or
      * every record granted away) has an all-zero row: skipped for all classes at once. */
-    const bool canSkip = Wn <= 32;                          /* one bit per cohort of the window */
-    unsigned liveSlots = canSkip ? 0u : 1u;
-    if (canSkip)
-        for (int d = 1; d < Wn; ++d) { const unsigned m = ((unsigned)(T + d) & Rm); if (S_bcount[m] != S_dead[m]) liveSlots |= 1u << d; }
+    const unsigned liveSlots = canSkip ? liveWin : 1u;
     unsigned nSing = 0;
     if (liveSlots) {
         int f[RW_LANES];

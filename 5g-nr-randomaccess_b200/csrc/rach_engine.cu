@@ -90,7 +90,7 @@ struct RaKernelArgs {
     int               nJobs, maxP, maxR;
 };
 
-template <bool DUMP, int NT, int MINB, bool FIXED>
+template <bool DUMP, int NT, int MINB, bool FIXED, bool TIMERS = false>
 __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
     /* FIXED: every point of the launch belongs to the reference's default family (54 preambles, BI 20, subframe 5, RAR
      * window 5): those values are immediates in this instantiation (RaPointDef); otherwise they are read from the point */
@@ -101,7 +101,9 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
     __shared__ int sLight[4];                           /* warp 0 -> block: ms to resume at, how (ra_light_ms code), simTime */
     __shared__ ra_u64 sCyc[RA_NPHASE];
     long long tick = 0;
-    const bool timers = a.phaseCycles != nullptr;     /* profiling aid (ra_options.phaseTimers), off by default */
+    /* profiling aid (ra_options.phaseTimers): its own instantiation, so that the product kernel carries none of the
+     * per-phase tests (a dozen per ms and warp: 9 % of the instructions of a lightly loaded ms) */
+    const bool timers = TIMERS && a.phaseCycles != nullptr;
     if (threadIdx.x < RA_NPHASE) sCyc[threadIdx.x] = 0;
     const int tid = threadIdx.x, nt = blockDim.x;
     const RaWork w = a.works[blockIdx.x];
@@ -494,14 +496,17 @@ struct RaDev {
 /* shape: 0 = 128 x 8, 1 = 256 x 5, 2 = 512 x 2 (threads x resident blocks per SM) */
 static const int kShapeNT[3] = {RA_NT, RA_NT_BIG, RA_NT_HUGE};
 static const int kShapeMinB[3] = {RA_MINB, RA_MINB_BIG, RA_MINB_HUGE};
-template <bool DUMP, bool FIXED>
+template <bool DUMP, bool FIXED, bool TIMERS>
 static const void* ra_step_entry2(int shape) {
-    if (shape == 2) return (const void*)ra_step_kernel<DUMP, RA_NT_HUGE, RA_MINB_HUGE, FIXED>;
-    return shape == 1 ? (const void*)ra_step_kernel<DUMP, RA_NT_BIG, RA_MINB_BIG, FIXED> : (const void*)ra_step_kernel<DUMP, RA_NT, RA_MINB, FIXED>;
+    if (shape == 2) return (const void*)ra_step_kernel<DUMP, RA_NT_HUGE, RA_MINB_HUGE, FIXED, TIMERS>;
+    return shape == 1 ? (const void*)ra_step_kernel<DUMP, RA_NT_BIG, RA_MINB_BIG, FIXED, TIMERS>
+                      : (const void*)ra_step_kernel<DUMP, RA_NT, RA_MINB, FIXED, TIMERS>;
 }
-static const void* ra_step_entry(bool dump, int shape, bool fixed) {
-    if (dump) return fixed ? ra_step_entry2<true, true>(shape) : ra_step_entry2<true, false>(shape);
-    return fixed ? ra_step_entry2<false, true>(shape) : ra_step_entry2<false, false>(shape);
+/* (the phase timers exist without the per-UE dump only: ra_sim_create refuses the combination) */
+static const void* ra_step_entry(bool dump, int shape, bool fixed, bool timers) {
+    if (dump) return fixed ? ra_step_entry2<true, true, false>(shape) : ra_step_entry2<true, false, false>(shape);
+    if (timers) return fixed ? ra_step_entry2<false, true, true>(shape) : ra_step_entry2<false, false, true>(shape);
+    return fixed ? ra_step_entry2<false, true, false>(shape) : ra_step_entry2<false, false, false>(shape);
 }
 
 struct ra_sim {
@@ -634,7 +639,7 @@ static int ra_setup_device(ra_sim* sim, RaDev& d) {
     d.nt = isN ? RA_NT_N : kShapeNT[shape];
     const int minb = isN ? RA_MINB_N : kShapeMinB[shape];
     const void* kern = isN ? (dump ? (const void*)ra_step_kernel_n<true> : (const void*)ra_step_kernel_n<false>)
-                           : ra_step_entry(dump, shape, fixed);
+                           : ra_step_entry(dump, shape, fixed, sim->opt.phaseTimers != 0);
     d.kern = kern;
     RA_CUDA(sim, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
     /* the driver's default carveout heuristic was the best of {default, 50, 60, 75, 100 %} (within 0.6 %);
@@ -717,6 +722,9 @@ extern "C" ra_sim* ra_sim_create_ex(const ra_params* points, int nPoints, int re
     ra_sim* sim = new ra_sim();
     memset(&sim->opt, 0, sizeof sim->opt);
     if (opt) sim->opt = *opt;
+    if (sim->opt.phaseTimers && sim->opt.dumpUEs) {
+        g_createErr = "phaseTimers and dumpUEs cannot be combined (the timed kernel is the one without the per-UE dump)"; delete sim; return nullptr;
+    }
     sim->nPoints = nPoints; sim->reps = repsPerPoint;
     sim->points.assign(points, points + nPoints);
     char err[256];

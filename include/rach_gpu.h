@@ -109,7 +109,8 @@ typedef struct ra_options {
     int repOffset;      /* tape replication id of local rep 0 (multi-process sharding)        */
     int dumpUEs;        /* 1 = keep the 16-int per-UE final record of every replication       */
     int ctasPerSM;      /* 0 = engine default; resident CTAs per SM of the step kernel        */
-    int phaseTimers;    /* 1 = collect per-phase cycle counters (ra_sim_phase_cycles); costs ~2 % */
+    int phaseTimers;    /* 1 = collect per-phase cycle counters (ra_sim_phase_cycles): a separate kernel instantiation
+                           (costs ~2 %), W/B dynamics only, not together with dumpUEs (RA_E_INVAL) */
     int reserved[4];
 } ra_options;
 
