@@ -258,6 +258,8 @@ struct RaWork {
 struct RaShared {
     int grantCheck, activeCheck, acOld, nArr, overflow, nextAc;   /* nextAc: activeCheck after the next arrival step */
     int nextArrMs, occ;       /* next ms with T % A == 0 and its occasion number (no division in the ms loop) */
+    int gcAdd;                /* singleton scans of the ms just finished that phase 5 did not have to rank (all answered):
+                                 added to grantCheck by the thread that opens the next ms (ra_gc_apply) */
     unsigned nLanders, nUnc, nC3, nSingles, nE1, nMov, nM3, tau;
     unsigned nSuccess, noGrant, nNl, nNlLight;      /* nNlLight: stale position hints met by ra_light_ms (its own counter:
                                                       the block may still be reading nNl of the ms it has just finished) */
@@ -480,7 +482,7 @@ RA_HD void ra_job_init(const RaJobT<PT>& job, RaShared& s, int tid, int nt) {
     for (int i = tid; i < RA_HBINS; i += nt) S_hist[i] = 0;
     if (DUMP) for (int i = tid; i < pt.nUE; i += nt) ra_dump_init_row(job.dump + (size_t)i * RA_DUMP_W);
     if (tid == 0) {
-        s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0;
+        s.grantCheck = 0; s.activeCheck = 0; s.overflow = 0; s.gcAdd = 0;
         s.nextAc = pt.arrCum[0]; s.nextArrMs = 0; s.occ = 0;
         s.nSuccess = 0; s.noGrant = 0;
         s.txSum = s.delaySum = s.failSum = s.contFailed = s.collP = s.txop = s.collScans = s.totScans = 0;
@@ -903,6 +905,18 @@ __device__ __forceinline__ void ra_phase5_warp(const PT& pt, const RaWork& w, Ra
 #endif
 
 RA_HD bool ra_granted(const RaShared& s, unsigned idx) { return !s.noGrant && idx <= s.tau; }
+
+/* Phase 5 is not needed when every singleton scan of the ms is answered (grantCheck + n < G, W:639-641): the flags the
+ * ms started with (tau = everybody, noGrant = 0) already say so.  Every thread evaluates this after phase 4 (same
+ * answer); one thread notes the count, and grantCheck itself is only touched once nobody reads it any more: by the
+ * thread that opens the next ms (ra_gc_apply).  Saves a block barrier in most ms of a lightly or moderately loaded cell. */
+template <class PT>
+RA_HD bool ra_phase5_trivial(const PT& pt, const RaShared& s) {
+    return (long long)s.nSingles <= (long long)pt.G - 1 - (long long)s.grantCheck;
+}
+RA_HD void ra_gc_apply(RaShared& s) {                            /* one thread, before the next ms reads grantCheck */
+    if (s.gcAdd) { s.grantCheck += s.gcAdd; s.gcAdd = 0; }
+}
 
 /* a granted visible non-mover leaves its bucket and cohort and queues Msg3 (W:642-645) */
 template <bool DUMP, class PT>

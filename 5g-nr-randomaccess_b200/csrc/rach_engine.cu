@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                 if (!first && ra_ms_done(pt, s, T, &simTime)) code = 4;           /* the ms the block has just finished */
                 else {
                     if (!first) ++T;
+                    if (tid == 0) ra_gc_apply(s);
                     if (RA_LIGHT) {
                         if (tid == 0) ra_lists_reset(s);
                         __syncwarp();
@@ -251,9 +252,13 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
             __syncthreads();
             RA_TICK(5);
             if (s.nSingles) {
-                if (tid < 32) ra_phase5_warp(pt, w, s, tid);
-                __syncthreads();
-                RA_TICK(6);
+                if (ra_phase5_trivial(pt, s)) {                    /* every scan answered: no threshold, no barrier */
+                    if (tid == 0) s.gcAdd = (int)s.nSingles;
+                } else {
+                    if (tid < 32) ra_phase5_warp(pt, w, s, tid);
+                    __syncthreads();
+                    RA_TICK(6);
+                }
             }
             {
                 const unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;

@@ -35,6 +35,7 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
         /* the kernel's control flow: warp 0 runs light ms back to back (ra_light_ms, vector form: the 32 lanes are played
          * by a loop), then prepares the first ms that needs the whole block */
         int code = 0;
+        ra_gc_apply(s);
         if (emu_light) {
             ra_lists_reset(s);
             RaCtl c = ra_ctl_load(s);
@@ -74,7 +75,7 @@ static int emu_body(const PT& pt, const RaWork& w, RaShared& s, const ref_config
         if (s.nE1) { unsigned n = s.nE1; for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n; i += NT) ra_phase3b_item(pt, w, s, i); }
         unsigned n4 = (unsigned)pt.P + s.nLanders;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n4; i += NT) ra_phase4_item(pt, w, s, acc[t], i);
-        if (s.nSingles) ra_phase5_serial(pt, w, s);
+        if (s.nSingles) { if (ra_phase5_trivial(pt, s)) s.gcAdd = (int)s.nSingles; else ra_phase5_serial(pt, w, s); }
         unsigned n6 = (unsigned)pt.P + s.nLanders + s.nE1;
         for (int t = 0; t < NT; ++t) for (unsigned i = t; i < n6; i += NT) ra_phase6_item<DUMP>(job, w, s, T, i);
         if (s.nSingles) for (int t = 0; t < NT; ++t) ra_hist_clear(pt, w, s, t, NT);
