@@ -197,14 +197,14 @@ __global__ void __launch_bounds__(NT, MINB) ra_step_kernel(RaKernelArgs a) {
                     for (int k = 0; k < RA_ILP; ++k) {
                         RaPend land;
                         const bool lands = ra_phase1_mover_d<DUMP>(job, w, s, acc, T, i + k * NT, c[k], d[k], land);
-#if RA_DEFER
-                        /* a second re-transmitter in a lane that still holds one: the whole warp empties its registers
-                         * (one pass of the list code for a dozen lanes instead of one pass per lane) */
-                        if (__any_sync(0xFFFFFFFFu, lands && pd.x != RA_INF32)) ra_pend_flush(pt, w, s, T, pd);
-                        if (lands) pd = land;
-#else
-                        if (lands) { pd = land; ra_pend_flush(pt, w, s, T, pd); }
-#endif
+                        if (RA_DEFER && FIXED) {
+                            /* a second re-transmitter in a lane that still holds one: the whole warp empties its registers
+                             * (one pass of the list code for a dozen lanes instead of one pass per lane).  Only with the
+                             * compile-time point view: with runtime parameters the three extra live registers cost more
+                             * than the branch (measured on the configs[4] grid: 1062 vs 1014 ms) */
+                            if (__any_sync(0xFFFFFFFFu, lands && pd.x != RA_INF32)) ra_pend_flush(pt, w, s, T, pd);
+                            if (lands) pd = land;
+                        } else if (lands) { pd = land; ra_pend_flush(pt, w, s, T, pd); }
                     }
 #pragma unroll
                     for (int k = 0; k < RA_ILP; ++k) c[k] = n[k];
