@@ -131,6 +131,10 @@ int ra_host_validate(const ra_params* p, char* err, size_t errLen) {
     if (p->accessTime < 1 || p->accessTime > 4096) RA_BAD("accessTime %d out of range [1, 4096]", p->accessTime);
     const int h = ra_horizon_ms(p);
     if (h < 1 || h > 65535) RA_BAD("horizon %d ms out of range [1, 65535]", h);
+    /* the engines index a replication's move calendar (ring x nUE records of 16 bytes) with 32 bits */
+    if (p->variant != RA_VARIANT_U0 && (unsigned long long)ra_host_ring(p) * (unsigned long long)p->nUE >= (1ull << 32))
+        RA_BAD("ring %d x nUE %d exceeds 2^32 calendar records per replication (64 GB): lower backoffIndicator / accessTime / nUE",
+               ra_host_ring(p), p->nUE);
 #undef RA_BAD
     return RA_OK;
 }

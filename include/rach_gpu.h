@@ -158,7 +158,10 @@ const char* ra_sim_last_error(const ra_sim* sim);
 int         ra_params_default(ra_params* p, int variant);   /* W:69-88 defaults */
 int         ra_horizon_ms(const ra_params* p);              /* W:243,254 */
 /* the parameter checks of ra_sim_create without a device: RA_OK, or RA_E_INVAL with the reason in err[errLen]
- * (the reference checks only "> 0" style ranges in main, W:94-158; the engine adds its packing limits) */
+ * (the reference checks only "> 0" style ranges in main, W:94-158; the engine adds its packing limits: nUE <= 2^24,
+ * nPreamble <= 256, backoffIndicator <= 4096, RAR window <= 255, max retx <= 256, horizon <= 65535 ms, and
+ * ring x nUE < 2^32 calendar records per replication, ring = next power of two >= backoffIndicator + max(accessTime, 5)
+ * + maxRarWindow) */
 int         ra_params_validate(const ra_params* p, char* err, int errLen);
 /* arrivals[ms] for ms in [0, horizon): UEs that become active in that ms (after the clamp of
  * W:290-292), 0 for ms % accessTime != 0.  Returns the ms at which all nUE have arrived, or -1. */

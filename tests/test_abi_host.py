@@ -116,6 +116,10 @@ def test_validation_without_a_device(pkg):
     assert pkg.validate_params(pkg.default_params(variant=2, cellRadius=35.5))[0] == 0
     # W never feeds the radius back into the dynamics (W:392-415 are side outputs): any value is accepted there
     assert pkg.validate_params(pkg.default_params(cellRadius=0.0))[0] == 0
+    # the move calendar of a replication is indexed with 32 bits: ring (next power of two of BI + subframe + window) x nUE
+    rc, msg = pkg.validate_params(pkg.default_params(nUE=1 << 24, backoffIndicator=4096))
+    assert rc == -1 and "calendar records" in msg
+    assert pkg.validate_params(pkg.default_params(nUE=1 << 24, backoffIndicator=100))[0] == 0      # 128 x 2^24 = 2^31
     rc, msg = pkg.validate_params(pkg.default_params(nPreamble=0))
     assert rc == -1 and "nPreamble" in msg
 
